@@ -1,0 +1,106 @@
+/*
+ * fv3_b200.h — C ABI of the B200-native FV3 dynamical-core hot path.
+ *
+ * Every entry point replaces one call of the reference (ai2cm/pace; file:line given per function) and keeps
+ * that call's argument order and meaning.  Rules of the boundary:
+ *   - plain C: pointers, sizes, scalars; no C++/torch types; no exceptions cross it;
+ *   - all array pointers are DEVICE pointers borrowed for the duration of the call (the Python side owns the
+ *     memory through pace_b200.util.Quantity / __cuda_array_interface__); nothing is allocated here;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*) and never synchronises;
+ *   - return value 0 = ok, otherwise a cudaError_t (or -1 for argument errors); fv3_last_error() gives text.
+ *
+ * Array layout ("batched I-fastest"): a 3-D field holds all local subdomains,
+ *     element (s, i, j, k) at  base[s*ss + k*sk + j*sj + i],   i, j include the halo (compute origin = halo),
+ * with storage extents ni = nx+2*halo+1, nj = ny+2*halo+1, nk = nz+1 for EVERY field (as the reference's
+ * SubtileGridSizer does, util/pace/util/initialization/sizer.py:142-155).  2-D fields use (s, i, j) at
+ * base[s*ss2 + j*sj + i].  Column vectors (ak, bk, dp_ref, pfull ...) are plain double[nk].
+ */
+#ifndef FV3_B200_H
+#define FV3_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FV3_MAX_SUBDOMAINS 64
+#define FV3_MAX_LEVELS 128
+#define FV3_EDGE_WEST 1
+#define FV3_EDGE_EAST 2
+#define FV3_EDGE_SOUTH 4
+#define FV3_EDGE_NORTH 8
+
+typedef struct fv3_geom {
+  int32_t n_sub;            /* local subdomains held by this process / GPU */
+  int32_t nx, ny, nz;       /* compute cells per subdomain */
+  int32_t halo;             /* 3 */
+  int32_t ni, nj, nk;       /* storage extents */
+  int32_t sj;               /* j stride (elements); i stride is 1 */
+  int32_t pad_;
+  int64_t sk, ss, ss2;      /* k stride, subdomain stride (3-D), subdomain stride (2-D) */
+  uint8_t edge[FV3_MAX_SUBDOMAINS]; /* FV3_EDGE_* bits: is subdomain s on that edge of its cube tile
+                                       (GridIndexing.west_edge..., dsl/pace/dsl/stencil.py:717-758) */
+} fv3_geom;
+
+/* Scalar namelist values read on the path (fv3core/pace/fv3core/_config.py:14-160). */
+typedef struct fv3_config {
+  int32_t hord_dp, hord_tm, hord_mt, hord_vt, hord_tr;
+  int32_t kord_tm, kord_tr, kord_wz, kord_mt;
+  int32_t nord, n_sponge, nwat, fill, do_vort_damp, convert_ke, hydrostatic, rf_fast;
+  int32_t ks;               /* GridData.ks */
+  double d2_bg, d2_bg_k1, d2_bg_k2, d4_bg, ke_bg, dddmp, vtdm4, d_con, delt_max;
+  double p_fac, a_imp, tau, rf_cutoff;
+  double ptop, da_min, da_min_c;
+} fv3_config;
+
+/* Device pointers to the 2-D metric terms of all local subdomains (util/pace/util/grid/helper.py:305-640)
+ * and the damping coefficients (helper.py:20-60); columns are double[nk]. */
+typedef struct fv3_grid {
+  const double *dx, *dy, *dxa, *dya, *dxc, *dyc, *rdx, *rdy, *rdxa, *rdya, *rdxc, *rdyc;
+  const double *area, *area_64, *rarea, *rarea_c;
+  const double *cosa, *cosa_u, *cosa_v, *cosa_s, *sina_u, *sina_v, *rsina, *rsin_u, *rsin_v, *rsin2;
+  const double *sin_sg1, *sin_sg2, *sin_sg3, *sin_sg4, *cos_sg1, *cos_sg2, *cos_sg3, *cos_sg4;
+  const double *fC, *f0;
+  const double *edge_w, *edge_e, *edge_s, *edge_n;       /* a2b_ord4 edge weights, stored as 2-D fields */
+  const double *divg_u, *divg_v, *del6_u, *del6_v;
+  const double *a11, *a12, *a21, *a22;
+  const double *ak, *bk, *dp_ref, *pfull;                /* columns */
+} fv3_grid;
+
+typedef struct fv3_ctx fv3_ctx;
+
+/* scratch: device buffer of scratch_bytes used for stage-private temporaries (never freed here). */
+fv3_ctx *fv3_create(const fv3_geom *geom, const fv3_config *config, const fv3_grid *grid, void *scratch,
+                    int64_t scratch_bytes);
+void fv3_destroy(fv3_ctx *ctx);
+const char *fv3_last_error(void);
+int fv3_abi_version(void);
+/* 1 when this library was built as the CPU host-simulation of the kernels (tests only), 0 for CUDA. */
+int fv3_is_hostsim(void);
+/* number of 3-D scratch fields fv3_create needs (scratch_bytes >= n * ss * n_sub * 8) */
+int fv3_scratch_fields(void);
+
+/* ---- halo exchange: replaces HaloUpdater.start/wait pack/unpack + the four NVRTC kernels
+ *      (util/pace/util/halo_updater.py:217-303, halo_data_transformer.py:537-921, cuda_kernels.py:5-178).
+ * One launch moves n_entries 2-D points x nlev levels x n_fields fields.  Entry e copies
+ *   dst = fields[dst_comp[e]*n_fields + f] + dst_off[e] (+ k*sk)  <-  sign[e] * (src likewise),
+ * offsets already include the subdomain stride.  fields holds n_comp*n_fields device pointers.        */
+int fv3_halo_gather(const fv3_geom *geom, double *const *fields, int n_fields, int nlev, const int64_t *dst_off,
+                    const int64_t *src_off, const int8_t *dst_comp, const int8_t *src_comp, const double *sign,
+                    int64_t n_entries, void *stream);
+/* pack: buf[(f*nlev + k)*n_entries + e] = sign[e] * src ;  unpack: dst = buf[...] (sign already applied) */
+int fv3_halo_pack(const fv3_geom *geom, double *const *fields, int n_fields, int nlev, const int64_t *src_off,
+                  const int8_t *src_comp, const double *sign, int64_t n_entries, double *buf, void *stream);
+int fv3_halo_unpack(const fv3_geom *geom, double *const *fields, int n_fields, int nlev, const int64_t *dst_off,
+                    const int8_t *dst_comp, int64_t n_entries, const double *buf, void *stream);
+
+/* ---- NonhydrostaticVerticalSolverCGrid.__call__ (fv3core/pace/fv3core/stencils/riem_solver_c.py:172-250) */
+int fv3_riem_solver_c(fv3_ctx *ctx, double dt2, const double *cappa, double ptop, const double *hs,
+                      const double *ws, const double *ptc, const double *q_con, const double *delpc, double *gz,
+                      double *pef, const double *w3, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FV3_B200_H */

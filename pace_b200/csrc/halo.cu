@@ -1,0 +1,42 @@
+// Halo exchange data movement: one launch per exchange for all fields x levels x local subdomains.
+// Replaces pack/unpack_scalar_f64, pack/unpack_vector_f64 (util/pace/util/cuda_kernels.py:5-178) and the
+// per-field/per-neighbour launch loops of HaloDataTransformerGPU (halo_data_transformer.py:694-915).
+// Rotation and vector sign/component swaps are folded into the host-built gather table
+// (pace_b200/util/topology.py), so the device side is a pure indexed copy.
+#include "common.h"
+
+extern "C" {
+
+int fv3_halo_gather(const fv3_geom *geom, double *const *fields, int n_fields, int nlev, const int64_t *dst_off,
+                    const int64_t *src_off, const int8_t *dst_comp, const int8_t *src_comp, const double *sign,
+                    int64_t n_entries, void *stream) {
+  const int64_t sk = nlev > 1 ? geom->sk : 0;
+  fv3::launch1d((cudaStream_t)stream, n_entries, nlev, n_fields, FV_LAMBDA(int64_t e, int k, int f) {
+    const double *src = fields[src_comp[e] * n_fields + f];
+    double *dst = fields[dst_comp[e] * n_fields + f];
+    dst[dst_off[e] + k * sk] = sign[e] * src[src_off[e] + k * sk];
+  });
+  return fv3::check_launch("fv3_halo_gather");
+}
+
+int fv3_halo_pack(const fv3_geom *geom, double *const *fields, int n_fields, int nlev, const int64_t *src_off,
+                  const int8_t *src_comp, const double *sign, int64_t n_entries, double *buf, void *stream) {
+  const int64_t sk = nlev > 1 ? geom->sk : 0;
+  fv3::launch1d((cudaStream_t)stream, n_entries, nlev, n_fields, FV_LAMBDA(int64_t e, int k, int f) {
+    const double *src = fields[src_comp[e] * n_fields + f];
+    buf[((int64_t)f * nlev + k) * n_entries + e] = sign[e] * src[src_off[e] + k * sk];
+  });
+  return fv3::check_launch("fv3_halo_pack");
+}
+
+int fv3_halo_unpack(const fv3_geom *geom, double *const *fields, int n_fields, int nlev, const int64_t *dst_off,
+                    const int8_t *dst_comp, int64_t n_entries, const double *buf, void *stream) {
+  const int64_t sk = nlev > 1 ? geom->sk : 0;
+  fv3::launch1d((cudaStream_t)stream, n_entries, nlev, n_fields, FV_LAMBDA(int64_t e, int k, int f) {
+    double *dst = fields[dst_comp[e] * n_fields + f];
+    dst[dst_off[e] + k * sk] = buf[((int64_t)f * nlev + k) * n_entries + e];
+  });
+  return fv3::check_launch("fv3_halo_unpack");
+}
+
+}  // extern "C"
