@@ -100,6 +100,13 @@ int fv3_riem_solver_c(fv3_ctx *ctx, double dt2, const double *cappa, double ptop
                       const double *ws, const double *ptc, const double *q_con, const double *delpc, double *gz,
                       double *pef, const double *w3, void *stream);
 
+/* ---- CGridShallowWaterDynamics.__call__ (fv3core/pace/fv3core/stencils/c_sw.py:607-766), including
+ *      DGrid2AGrid2CGridVectors (d2a2c_vect.py:547-655).  delpc/ptc are the stage's own outputs
+ *      (self.delpc, self.ptc in the reference, returned by __call__). */
+int fv3_c_sw(fv3_ctx *ctx, double *delp, double *pt, const double *u, const double *v, double *w, double *uc,
+             double *vc, double *ua, double *va, double *ut, double *vt, double *divgd, double *omga, double *delpc,
+             double *ptc, double dt2, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

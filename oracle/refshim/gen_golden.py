@@ -1,6 +1,6 @@
 """Generate golden vectors from the UNMODIFIED reference (numpy backend) — run in the build container only.
 
-    PYTHONPATH=/root/repo python -m oracle.refshim.gen_golden --nx 12 --layout 1 --out tests/golden/_cache/c12
+    PYTHONPATH=/root/repo python -m oracle.refshim.gen_golden --nx 12 --layout 1 --out /tmp/pace_b200_golden/c12
 
 Writes (np.savez, fp64, full arrays incl. halos, reference memory order [i, j, k]):
   grid_rank{r}.npz     every GridData / DampingCoefficients term of rank r

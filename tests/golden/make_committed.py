@@ -34,7 +34,7 @@ def reduce_stage(src, dst):
 def main():
     case, rank = sys.argv[1], int(sys.argv[2])
     stages = sys.argv[3:]
-    src = os.path.join(HERE, "_cache", case)
+    src = os.path.join(os.environ.get("PACE_B200_GOLDEN_CACHE", "/tmp/pace_b200_golden"), case)
     dst = os.path.join(HERE, case)
     os.makedirs(os.path.join(dst, f"stage_rank{rank}"), exist_ok=True)
     shutil.copy(os.path.join(src, "meta.json"), os.path.join(dst, "meta.json"))

@@ -10,7 +10,7 @@ from pace_b200.util.sizer import QuantityFactory, SubtileGridSizer
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-CACHE = os.path.join(GOLDEN, "_cache")
+CACHE = os.environ.get("PACE_B200_GOLDEN_CACHE", "/tmp/pace_b200_golden")  # uncommitted full reference dumps
 
 D3 = (c.X_DIM, c.Y_DIM, c.Z_DIM)
 D3I = (c.X_DIM, c.Y_DIM, c.Z_INTERFACE_DIM)
