@@ -107,6 +107,17 @@ int fv3_c_sw(fv3_ctx *ctx, double *delp, double *pt, const double *u, const doub
              double *vc, double *ua, double *va, double *ut, double *vt, double *divgd, double *omga, double *delpc,
              double *ptc, double dt2, void *stream);
 
+/* ---- UpdateGeopotentialHeightOnCGrid.__call__ (updatedzc.py:167-207); dp_ref and area come from fv3_grid */
+int fv3_update_dz_c(fv3_ctx *ctx, const double *zs, const double *ut, const double *vt, double *gz, double *ws,
+                    double dt, void *stream);
+/* ---- p_grad_c_stencil (dyn_core.py:120-171), non-hydrostatic */
+int fv3_p_grad_c(fv3_ctx *ctx, const double *rdxc, const double *rdyc, double *uc, double *vc, const double *delpc,
+                 const double *pkc, const double *gz, double dt2, void *stream);
+/* ---- small AcousticDynamics stencils (dyn_core.py:83-117) */
+int fv3_gz_from_delz(fv3_ctx *ctx, const double *zs, const double *delz, double *gz, void *stream);
+int fv3_pem_from_delp(fv3_ctx *ctx, const double *delp, double *pem, double ptop, void *stream);
+int fv3_compute_geopotential(fv3_ctx *ctx, const double *zh, double *gz, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -114,6 +114,13 @@ def wrap_callable(fn, stage, capture, skip_self=True, extra=None):
             names = {f"arg{i}": a for i, a in enumerate(args)}
             names.update(kwargs)
         selfobj = names.pop("self", None)
+        # FrozenStencil.__call__(*args, **kwargs): name positional args after the stencil definition's parameters
+        if "args" in names and isinstance(names["args"], tuple):
+            pos = names.pop("args")
+            kw = names.pop("kwargs", {}) or {}
+            argn = getattr(fn, "_argument_names", None) or getattr(getattr(fn, "__self__", None), "_argument_names", None) or [f"arg{i}" for i in range(len(pos))]
+            names = dict(zip(argn, pos))
+            names.update(kw)
         rec = {"in": {}, "out": {}}
         for k, v in names.items():
             _flatten(k, _snap(v), rec["in"])

@@ -1,0 +1,137 @@
+"""Registry of hot-path stages: golden file, oracle call, native call, outputs, tolerance.
+
+Each spec is used three ways by tests/test_stages.py: oracle vs reference golden, native kernels (host
+simulation on CPU boxes / CUDA on the GPU box) vs golden, and native vs oracle.
+"""
+import dataclasses
+from typing import Callable, Dict, Sequence
+
+import numpy as np
+
+from oracle.indexing import Idx
+from tests import helpers as H
+
+NX = 12
+NZ = 79
+
+
+@dataclasses.dataclass
+class StageSpec:
+    name: str
+    golden: str                       # stage file name, e.g. "C_SW#0"
+    outputs: Sequence[str]
+    oracle: Callable                  # (ix, grid: dict, a: dict of numpy arrays) -> None (in place; may add keys)
+    native: Callable                  # (sf, qf, rt, q: dict of Quantity, d: golden dict) -> None (may add keys)
+    tol: float = 1e-14                # reference metric, native vs golden
+    near_zero: float = 1e-18
+    oracle_tol: float = 1e-14
+    interface_fields: Sequence[str] = ()
+
+
+SPECS: Dict[str, StageSpec] = {}
+
+
+def register(spec: StageSpec):
+    SPECS[spec.name] = spec
+    return spec
+
+
+def f(d, key):
+    return float(d["in." + key])
+
+
+# ---------------------------------------------------------------------------------------------
+def _o_riem_c(ix, g, a):
+    from oracle import riem_solver as O
+
+    O.riem_solver_c(float(a["dt2"]), a["cappa"], float(a["ptop"]), a["hs"], a["ws"], a["ptc"], a["q_con"], a["delpc"],
+                    a["gz"], a["pef"], a["w3"], 0.05, ix.nx, ix.ny, ix.nz)
+
+
+def _n_riem_c(sf, qf, rt, q, d):
+    from pace_b200.fv3core.stencils.riem_solver_c import NonhydrostaticVerticalSolverCGrid
+
+    NonhydrostaticVerticalSolverCGrid(sf, qf, 0.05)(f(d, "dt2"), q["cappa"], f(d, "ptop"), q["hs"], q["ws"], q["ptc"],
+                                                    q["q_con"], q["delpc"], q["gz"], q["pef"], q["w3"])
+
+
+register(StageSpec("riem_solver_c", "Riem_Solver_C#0", ("gz", "pef"), _o_riem_c, _n_riem_c, tol=1e-12))
+
+
+def _o_c_sw(ix, g, a):
+    from oracle import c_sw as O
+
+    a["delpc"], a["ptc"] = O.c_sw(ix, g, a["delp"], a["pt"], a["u"], a["v"], a["w"], a["uc"], a["vc"], a["ua"], a["va"],
+                                  a["ut"], a["vt"], a["divgd"], a["omga"], float(a["dt2"]))
+
+
+def _n_c_sw(sf, qf, rt, q, d):
+    from pace_b200.fv3core.stencils.c_sw import CGridShallowWaterDynamics
+
+    csw = CGridShallowWaterDynamics(sf, qf, rt.grid_data, False, 0, 3)
+    q["delpc"], q["ptc"] = csw(q["delp"], q["pt"], q["u"], q["v"], q["w"], q["uc"], q["vc"], q["ua"], q["va"], q["ut"],
+                               q["vt"], q["divgd"], q["omga"], f(d, "dt2"))
+
+
+register(StageSpec("c_sw", "C_SW#0", ("delp", "pt", "w", "uc", "vc", "ua", "va", "ut", "vt", "divgd", "omga", "delpc", "ptc"),
+                   _o_c_sw, _n_c_sw))
+
+
+def _o_dzc(ix, g, a):
+    from oracle import updatedz as O
+
+    O.update_dz_c(ix, g["dp_ref"], a["zs"], g["area"], a["ut"], a["vt"], a["gz"], a["ws"], float(a["dt"]))
+
+
+def _n_dzc(sf, qf, rt, q, d):
+    from pace_b200.fv3core.stencils.updatedzc import UpdateGeopotentialHeightOnCGrid
+
+    UpdateGeopotentialHeightOnCGrid(sf, qf, rt.grid_data.area, rt.grid_data.dp_ref)(q["zs"], q["ut"], q["vt"], q["gz"],
+                                                                                      q["ws"], f(d, "dt"))
+
+
+register(StageSpec("update_dz_c", "UpdateDzC#0", ("gz", "ws"), _o_dzc, _n_dzc))
+
+
+def _o_pgc(ix, g, a):
+    from oracle import dyn_core as O
+
+    O.p_grad_c(ix, a["rdxc"], a["rdyc"], a["uc"], a["vc"], a["delpc"], a["pkc"], a["gz"], float(a["dt2"]))
+
+
+def _n_pgc(sf, qf, rt, q, d):
+    rt.call("fv3_p_grad_c", q["rdxc"].ptr, q["rdyc"].ptr, q["uc"].ptr, q["vc"].ptr, q["delpc"].ptr, q["pkc"].ptr,
+            q["gz"].ptr, f(d, "dt2"))
+
+
+register(StageSpec("p_grad_c", "PGradC#0", ("uc", "vc"), _o_pgc, _n_pgc))
+
+
+def _o_gzdelz(ix, g, a):
+    from oracle import dyn_core as O
+
+    O.gz_from_surface_height_and_thicknesses(ix, a["zs"], a["delz"], a["gz"])
+
+
+register(StageSpec("gz_from_delz", "GzFromDelz#0", ("gz",), _o_gzdelz,
+                   lambda sf, qf, rt, q, d: rt.call("fv3_gz_from_delz", q["zs"].ptr, q["delz"].ptr, q["gz"].ptr)))
+
+
+def _o_pem(ix, g, a):
+    from oracle import dyn_core as O
+
+    O.interface_pressure_from_toa_pressure_and_thickness(ix, a["delp"], a["pem"], float(a["ptop"]))
+
+
+register(StageSpec("pem_from_delp", "PemFromDelp#0", ("pem",), _o_pem,
+                   lambda sf, qf, rt, q, d: rt.call("fv3_pem_from_delp", q["delp"].ptr, q["pem"].ptr, f(d, "ptop"))))
+
+
+def _o_geop(ix, g, a):
+    from oracle import dyn_core as O
+
+    O.compute_geopotential(ix, a["zh"], a["gz"])
+
+
+register(StageSpec("compute_geopotential", "ComputeGeopotential#0", ("gz",), _o_geop,
+                   lambda sf, qf, rt, q, d: rt.call("fv3_compute_geopotential", q["zh"].ptr, q["gz"].ptr)))
