@@ -118,6 +118,10 @@ int fv3_gz_from_delz(fv3_ctx *ctx, const double *zs, const double *delz, double 
 int fv3_pem_from_delp(fv3_ctx *ctx, const double *delp, double *pem, double ptop, void *stream);
 int fv3_compute_geopotential(fv3_ctx *ctx, const double *zh, double *gz, void *stream);
 
+/* ---- FiniteVolumeFluxPrep.__call__ (fv3core/pace/fv3core/stencils/fxadv.py:565-661) */
+int fv3_fv_prep(fv3_ctx *ctx, const double *uc, const double *vc, double *crx, double *cry, double *xfx, double *yfx,
+                double *uc_contra, double *vc_contra, double dt, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

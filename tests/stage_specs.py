@@ -26,6 +26,7 @@ class StageSpec:
     near_zero: float = 1e-18
     oracle_tol: float = 1e-14
     interface_fields: Sequence[str] = ()
+    regions: Dict[str, tuple] = dataclasses.field(default_factory=dict)  # output -> (i slice, j slice) compared
 
 
 SPECS: Dict[str, StageSpec] = {}
@@ -135,3 +136,22 @@ def _o_geop(ix, g, a):
 
 register(StageSpec("compute_geopotential", "ComputeGeopotential#0", ("gz",), _o_geop,
                    lambda sf, qf, rt, q, d: rt.call("fv3_compute_geopotential", q["zh"].ptr, q["gz"].ptr)))
+
+
+def _o_fxadv(ix, g, a):
+    from oracle import fxadv as O
+
+    O.fv_prep(ix, g, a["uc"], a["vc"], a["crx"], a["cry"], a["x_area_flux"], a["y_area_flux"], a["uc_contra"],
+              a["vc_contra"], float(a["dt"]))
+
+
+def _n_fxadv(sf, qf, rt, q, d):
+    rt.call("fv3_fv_prep", q["uc"].ptr, q["vc"].ptr, q["crx"].ptr, q["cry"].ptr, q["x_area_flux"].ptr,
+            q["y_area_flux"].ptr, q["uc_contra"].ptr, q["vc_contra"].ptr, f(d, "dt"))
+
+
+# uc_contra / vc_contra are compared where they are consumed downstream (the reference leaves stale data
+# from the previous call in a few halo points next to tile edges, fxadv.py:33-48)
+register(StageSpec("fv_prep", "FxAdv#0", ("crx", "cry", "x_area_flux", "y_area_flux", "uc_contra", "vc_contra"),
+                   _o_fxadv, _n_fxadv,
+                   regions={"uc_contra": (slice(3, 3 + NX + 1), slice(None)), "vc_contra": (slice(None), slice(3, 3 + NX + 1))}))
