@@ -122,6 +122,19 @@ int fv3_compute_geopotential(fv3_ctx *ctx, const double *zh, double *gz, void *s
 int fv3_fv_prep(fv3_ctx *ctx, const double *uc, const double *vc, double *crx, double *cry, double *xfx, double *yfx,
                 double *uc_contra, double *vc_contra, double dt, void *stream);
 
+/* ---- FiniteVolumeTransport.__call__ (fvtp2d.py:235-346).  Optional (may be NULL): x/y_mass_flux, mass,
+ *      and the per-level columns nord_col / damp_col (device double[nk]) that switch on DelnFlux
+ *      (delnflux.py:1164-1207; damp_col = calc_damp(damp_c, da_min, nord), delnflux.py:18-33; nmax = max nord).
+ *      nk = number of levels (nz, or nz+1 for interface fields).  Valid outputs: fx on [isc..iec+1]x[jsc..jec],
+ *      fy on [isc..iec]x[jsc..jec+1].  q is not modified (the reference rewrites q's cube-corner halo cells). */
+int fv3_fvtp2d(fv3_ctx *ctx, const double *q, const double *crx, const double *cry, const double *xfx,
+               const double *yfx, double *fx, double *fy, const double *x_mass_flux, const double *y_mass_flux,
+               const double *mass, int hord, const double *nord_col, const double *damp_col, int nmax, int nk,
+               void *stream);
+/* ---- DelnFluxNoSG.__call__ (delnflux.py:1209-1261) with mass=None: fx2, fy2 <- del-n fluxes of damp*q */
+int fv3_delnflux_nosg(fv3_ctx *ctx, const double *q, double *fx2, double *fy2, const double *damp_col,
+                      const double *nord_col, int nmax, int nk, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,6 +27,7 @@ class StageSpec:
     oracle_tol: float = 1e-14
     interface_fields: Sequence[str] = ()
     regions: Dict[str, tuple] = dataclasses.field(default_factory=dict)  # output -> (i slice, j slice) compared
+    check_untouched: bool = True
 
 
 SPECS: Dict[str, StageSpec] = {}
@@ -155,3 +156,70 @@ def _n_fxadv(sf, qf, rt, q, d):
 register(StageSpec("fv_prep", "FxAdv#0", ("crx", "cry", "x_area_flux", "y_area_flux", "uc_contra", "vc_contra"),
                    _o_fxadv, _n_fxadv,
                    regions={"uc_contra": (slice(3, 3 + NX + 1), slice(None)), "vc_contra": (slice(None), slice(3, 3 + NX + 1))}))
+
+
+# ---------------------------------------------------------------------------------------------
+# fvtp2d: golden call n -> (hord, nord column, damp column, levels); order of calls in d_sw.py:935-1237,
+# updatedzd.py:283-356 and tracer_2d_1l.py:264-392
+FVTP2D_CASES = {0: (6, "nord_v", "damp_vt", NZ), 1: (6, None, None, NZ), 2: (6, "nord_t", "damp_t", NZ),
+                3: (6, "nord_v", "damp_vt", NZ), 4: (6, None, None, NZ), 5: (6, None, None, NZ + 1),
+                6: (8, None, None, NZ)}
+FLUX_REGIONS = {"q_x_flux": (slice(3, 3 + NX + 1), slice(3, 3 + NX)), "q_y_flux": (slice(3, 3 + NX), slice(3, 3 + NX + 1))}
+
+
+def _columns():
+    from pace_b200.fv3core._config import baroclinic_config
+    from pace_b200.fv3core.stencils.d_sw import get_column_namelist
+
+    return get_column_namelist(baroclinic_config(NX).d_grid_shallow_water, NZ)
+
+
+def _make_fvtp2d(n):
+    hord, no, da, nk = FVTP2D_CASES[n]
+
+    def oracle(ix, g, a):
+        from oracle import fvtp2d as O
+
+        col = _columns()
+        O.fvtp2d(ix, g, a["q"], a["crx"], a["cry"], a["x_area_flux"], a["y_area_flux"], a["q_x_flux"], a["q_y_flux"],
+                 hord, nk, a.get("x_mass_flux"), a.get("y_mass_flux"), a.get("mass"), col[no] if no else None,
+                 col[da] if da else None, float(g["damp_da_min"]))
+
+    def native(sf, qf, rt, q, d):
+        from pace_b200.fv3core.stencils.fvtp2d import FiniteVolumeTransport
+
+        col = _columns()
+        tp = FiniteVolumeTransport(sf, qf, rt.grid_data, rt.damping, 0, hord, col[no] if no else None,
+                                   col[da] if da else None)
+        tp(q["q"], q["crx"], q["cry"], q["x_area_flux"], q["y_area_flux"], q["q_x_flux"], q["q_y_flux"],
+           q.get("x_mass_flux"), q.get("y_mass_flux"), q.get("mass"), nk=nk)
+
+    register(StageSpec(f"fvtp2d_{n}", f"FvTp2d#{n}", ("q_x_flux", "q_y_flux"), oracle, native, regions=FLUX_REGIONS,
+                       check_untouched=False))
+
+
+for _n in FVTP2D_CASES:
+    _make_fvtp2d(_n)
+
+
+def _make_delnflux(n, nord_name):
+    def oracle(ix, g, a):
+        from oracle import fvtp2d as O
+
+        O.delnflux_nosg(ix, g, a["q"], a["fx2"], a["fy2"], a["damp_c"], _columns()[nord_name], NZ, d2=a["d2"])
+
+    def native(sf, qf, rt, q, d):
+        import torch
+
+        from pace_b200.fv3core.stencils.fvtp2d import DelnFluxNoSG, _column
+
+        dn = DelnFluxNoSG(sf, rt.damping, rt.grid_data.rarea, _columns()[nord_name])
+        dn(q["q"], q["fx2"], q["fy2"], _column(rt, d["in.damp_c"][:NZ]))
+
+    register(StageSpec(f"delnflux_nosg_{n}", f"DelnFluxNoSG#{n}", ("fx2", "fy2"), oracle, native,
+                       regions={"fx2": (slice(3, 3 + NX + 1), slice(3, 3 + NX)), "fy2": (slice(3, 3 + NX), slice(3, 3 + NX + 1))},
+                       check_untouched=False))
+
+
+_make_delnflux(0, "nord_w")
+_make_delnflux(1, "nord_v")

@@ -32,7 +32,8 @@ def test_oracle_matches_reference(name):
     a = {k[3:]: v.copy() for k, v in d.items() if k.startswith("in.")}
     spec.oracle(Idx(NX, NX, NZ), _grid(), a)
     for n in spec.outputs:
-        H.assert_close(a[n], d["out." + n], spec.oracle_tol, spec.near_zero, name=f"{name}.{n}")
+        reg = spec.regions.get(n, (slice(None), slice(None)))
+        H.assert_close(a[n][reg], d["out." + n][reg], spec.oracle_tol, spec.near_zero, name=f"{name}.{n}")
 
 
 def run_native(spec, d):
@@ -50,7 +51,7 @@ def _check_native(spec):
         reg = spec.regions.get(n, (slice(None), slice(None)))
         H.assert_close(q[n].numpy()[0][reg], d["out." + n][reg], spec.tol, spec.near_zero, name=f"{spec.name}.{n}")
     # inputs that the reference leaves untouched must be untouched here as well
-    for k, v in d.items():
+    for k, v in (d.items() if spec.check_untouched else ()):
         n = k[3:]
         if k.startswith("in.") and v.ndim >= 2 and n not in spec.outputs and np.array_equal(v, d["out." + n], equal_nan=True):
             np.testing.assert_array_equal(q[n].numpy()[0], v, err_msg=f"{spec.name}: input {n} was modified")
