@@ -66,7 +66,21 @@ typedef struct fv3_grid {
   const double *divg_u, *divg_v, *del6_u, *del6_v;
   const double *a11, *a12, *a21, *a22;
   const double *ak, *bk, *dp_ref, *pfull;                /* columns */
+  const double *a2b_w;  /* [n_sub][4 corners sw,se,nw,ne][3 arms] great-circle extrapolation weights x1/(x2-x1)
+                           of a2b_ord4.extrap_corner (a2b_ord4.py:37-56), computed once on the host */
 } fv3_grid;
+
+/* Per-level damping parameters of d_sw (get_column_namelist, d_sw.py:611-683) as device columns double[>= nz+1],
+ * plus the del-n coefficient columns derived from them with calc_damp (delnflux.py:18-33) on the host. */
+typedef struct fv3_dsw_cols {
+  const double *nord, *nord_v, *nord_w, *nord_t, *damp_vt, *damp_w, *damp_t, *d_con, *ke_bg, *d2_divg;
+  const double *dn_damp_vt;    /* calc_damp(damp_vt, da_min,   nord_v): DelnFlux inside fvtp2d_dp / fvtp2d_tm */
+  const double *dn_damp_t;     /* calc_damp(damp_t,  da_min,   nord_t): DelnFlux inside fvtp2d_dp_t */
+  const double *dn_damp_vt_c;  /* calc_damp(damp_vt, da_min_c, nord_v): delnflux_nosg_v (d_sw.py:915-919) */
+  const double *dn_damp_w_c;   /* calc_damp(damp_w,  da_min_c, nord_w): delnflux_nosg_w (d_sw.py:920-924) */
+  int32_t nmax_v, nmax_w, nmax_t;        /* max over levels of the nord columns */
+  int32_t nonzero_nord_k, nonzero_nord;  /* first level with nord > 0 and its nord (divergence_damping.py:216-223) */
+} fv3_dsw_cols;
 
 typedef struct fv3_ctx fv3_ctx;
 
@@ -134,6 +148,20 @@ int fv3_fvtp2d(fv3_ctx *ctx, const double *q, const double *crx, const double *c
 /* ---- DelnFluxNoSG.__call__ (delnflux.py:1209-1261) with mass=None: fx2, fy2 <- del-n fluxes of damp*q */
 int fv3_delnflux_nosg(fv3_ctx *ctx, const double *q, double *fx2, double *fy2, const double *damp_col,
                       const double *nord_col, int nmax, int nk, void *stream);
+
+/* ---- AGrid2BGridFourthOrder.__call__ (a2b_ord4.py:673-761) on levels [kstart, kstart+nk); qout != qin */
+int fv3_a2b_ord4(fv3_ctx *ctx, const double *qin, double *qout, int kstart, int nk, void *stream);
+/* ---- DivergenceDamping.__call__ (divergence_damping.py:482-632); uc/vc are inputs only here (the reference
+ *      also uses them as scratch for the Laplacian iterations) */
+int fv3_divergence_damping(fv3_ctx *ctx, const double *u, const double *v, const double *va,
+                           double *damped_rel_vort_bgrid, const double *ua, double *divg_d, const double *vc,
+                           const double *uc, double *delpc, double *ke, const double *rel_vort_agrid, double dt,
+                           const fv3_dsw_cols *cols, void *stream);
+/* ---- DGridShallowWaterLagrangianDynamics.__call__ (d_sw.py:935-1237), same argument order */
+int fv3_d_sw(fv3_ctx *ctx, double *delpc, double *delp, double *pt, double *u, double *v, double *w, double *uc,
+             double *vc, const double *ua, const double *va, double *divgd, double *mfx, double *mfy, double *cx,
+             double *cy, double *crx, double *cry, double *xfx, double *yfx, double *q_con, const double *zh,
+             double *heat_source, double *diss_est, double dt, const fv3_dsw_cols *cols, void *stream);
 
 #ifdef __cplusplus
 }

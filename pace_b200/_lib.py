@@ -41,11 +41,21 @@ GRID_FIELDS = [
     "divg_u", "divg_v", "del6_u", "del6_v",
     "a11", "a12", "a21", "a22",
     "ak", "bk", "dp_ref", "pfull",
+    "a2b_w",
 ]
 
 
 class Grid(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in GRID_FIELDS]
+
+
+DSW_COLS_PTR = ["nord", "nord_v", "nord_w", "nord_t", "damp_vt", "damp_w", "damp_t", "d_con", "ke_bg", "d2_divg",
+                "dn_damp_vt", "dn_damp_t", "dn_damp_vt_c", "dn_damp_w_c"]
+DSW_COLS_INT = ["nmax_v", "nmax_w", "nmax_t", "nonzero_nord_k", "nonzero_nord"]
+
+
+class DswCols(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in DSW_COLS_PTR] + [(n, C.c_int32) for n in DSW_COLS_INT]
 
 
 _lib = None

@@ -1,0 +1,441 @@
+// D-grid shallow-water Lagrangian dynamics (the hottest stage of the acoustic substep).
+//   fv3_d_sw               <- DGridShallowWaterLagrangianDynamics.__call__ (fv3core/pace/fv3core/stencils/d_sw.py:935-1237)
+//   fv3_divergence_damping <- DivergenceDamping.__call__ (divergence_damping.py:482-632)
+//   fv3_a2b_ord4           <- AGrid2BGridFourthOrder.__call__ (a2b_ord4.py:673-761)
+// Sub-stages call the same internal routines as the stand-alone entry points (fxadv.cu, fvtp2d.cu).
+#include "a2b.h"
+#include "common.h"
+#include "ppm.h"
+
+extern "C" int fv3_fv_prep(fv3_ctx *, const double *, const double *, double *, double *, double *, double *, double *,
+                           double *, double, void *);
+extern "C" int fv3_fvtp2d(fv3_ctx *, const double *, const double *, const double *, const double *, const double *,
+                          double *, double *, const double *, const double *, const double *, int, const double *,
+                          const double *, int, int, void *);
+extern "C" int fv3_delnflux_nosg(fv3_ctx *, const double *, double *, double *, const double *, const double *, int,
+                                 int, void *);
+
+namespace {
+
+constexpr double DCON_THRESHOLD = 1e-5;
+
+struct Ix {
+  int isc, iec, jsc, jec, ied, jed;
+};
+Ix make_ix(const fv3_geom &g) {
+  Ix x;
+  x.isc = g.halo;
+  x.iec = g.halo + g.nx - 1;
+  x.jsc = g.halo;
+  x.jec = g.halo + g.ny - 1;
+  x.ied = x.iec + g.halo;
+  x.jed = x.jec + g.halo;
+  return x;
+}
+
+// fill_corners_bgrid_x/y (corners.py:591-702) as read-time remaps on a B-grid (corner-point) field
+FV_HD void bgrid_corner_x(const fv3_geom &g, int s, int &i, int &j) {
+  const int isc = g.halo, ic = g.halo + g.nx, jsc = g.halo, jc = g.halo + g.ny;  // ic/jc: east / north corner point
+  const bool xo_w = i < isc, xo_e = i > ic, yo_s = j < jsc, yo_n = j > jc;
+  if (!((xo_w || xo_e) && (yo_s || yo_n))) return;
+  if (!((xo_w ? fv3::on_west(g, s) : fv3::on_east(g, s)) && (yo_s ? fv3::on_south(g, s) : fv3::on_north(g, s)))) return;
+  const int a = xo_w ? isc - i : i - ic, b = yo_s ? jsc - j : j - jc;
+  i = xo_w ? isc - b : ic + b;
+  j = yo_s ? jsc + a : jc - a;
+}
+FV_HD void bgrid_corner_y(const fv3_geom &g, int s, int &i, int &j) {
+  const int isc = g.halo, ic = g.halo + g.nx, jsc = g.halo, jc = g.halo + g.ny;
+  const bool xo_w = i < isc, xo_e = i > ic, yo_s = j < jsc, yo_n = j > jc;
+  if (!((xo_w || xo_e) && (yo_s || yo_n))) return;
+  if (!((xo_w ? fv3::on_west(g, s) : fv3::on_east(g, s)) && (yo_s ? fv3::on_south(g, s) : fv3::on_north(g, s)))) return;
+  const int a = xo_w ? isc - i : i - ic, b = yo_s ? jsc - j : j - jc;
+  i = xo_w ? isc + b : ic - b;
+  j = yo_s ? jsc - a : jc + a;
+}
+
+void a2b_ord4_launch(const fv3_ctx *ctx, cudaStream_t st, const double *qin, double *qout, int k0, int k1) {
+  const fv3_geom g = ctx->g;
+  const fv3_grid m = ctx->m;
+  const Ix x = make_ix(g);
+  fv3::launch3d(ctx, st, x.isc, x.iec + 2, x.jsc, x.jec + 2, k0, k1, FV_LAMBDA(int s, int i, int j, int k) {
+    auto q = [&](int ii, int jj) { return qin[O3(s, ii, jj, k)]; };
+    qout[O3(s, i, j, k)] = fv3::a2b_point(g, m, s, q, i, j);
+  });
+}
+
+// one iteration of the divergence-damping Laplacian (divergence_damping.py:566-589) for levels [k0, nz):
+// dnew <- rarea_c * div( grad(dold) scaled by divg_u / divg_v ), cube-corner fills folded in as remaps.
+void divg_iteration(const fv3_ctx *ctx, cudaStream_t st, const double *dold, double *dnew, int nt, bool fillc, int k0) {
+  const fv3_geom g = ctx->g;
+  const fv3_grid m = ctx->m;
+  const Ix x = make_ix(g);
+  const int isc = x.isc, iec = x.iec, jsc = x.jsc, jec = x.jec;
+  fv3::launch3d(ctx, st, isc - nt, iec + nt + 2, jsc - nt, jec + nt + 2, k0, g.nz, FV_LAMBDA(int s, int i, int j, int k) {
+    const bool W = fv3::on_west(g, s), E = fv3::on_east(g, s), S = fv3::on_south(g, s), N = fv3::on_north(g, s);
+    auto dgx = [&](int ii, int jj) {
+      if (fillc) bgrid_corner_x(g, s, ii, jj);
+      return dold[O3(s, ii, jj, k)];
+    };
+    auto dgy = [&](int ii, int jj) {
+      if (fillc) bgrid_corner_y(g, s, ii, jj);
+      return dold[O3(s, ii, jj, k)];
+    };
+    auto vc_raw = [&](int ii, int jj) { return (dgx(ii + 1, jj) - dgx(ii, jj)) * m.divg_u[O2(s, ii, jj)]; };
+    auto uc_raw = [&](int ii, int jj) { return (dgy(ii, jj + 1) - dgy(ii, jj)) * m.divg_v[O2(s, ii, jj)]; };
+    // fill_corners_dgrid_defn(vc, vc, uc, uc, -1) (corners.py:987-1151): x-field = vc (x centre, y interface),
+    // y-field = uc (x interface, y centre)
+    auto vc_at = [&](int ii, int jj) {
+      if (fillc) {
+        const bool xo_w = ii < isc, xo_e = ii > iec, yo_s = jj < jsc, yo_n = jj > jec + 1;
+        if ((xo_w || xo_e) && (yo_s || yo_n) && (xo_w ? W : E) && (yo_s ? S : N)) {
+          const int a = xo_w ? isc - ii : ii - iec, b = yo_s ? jsc - jj : jj - (jec + 1);
+          const double sg = (xo_w == yo_s) ? -1.0 : 1.0;  // sw, ne: mysign; nw, se: +1
+          const int si = xo_w ? isc - b : iec + 1 + b;
+          const int sjj = yo_s ? jsc + a - 1 : jec + 1 - a;
+          return sg * uc_raw(si, sjj);
+        }
+      }
+      return vc_raw(ii, jj);
+    };
+    auto uc_at = [&](int ii, int jj) {
+      if (fillc) {
+        const bool xo_w = ii < isc, xo_e = ii > iec + 1, yo_s = jj < jsc, yo_n = jj > jec;
+        if ((xo_w || xo_e) && (yo_s || yo_n) && (xo_w ? W : E) && (yo_s ? S : N)) {
+          const int a = xo_w ? isc - ii : ii - (iec + 1), b = yo_s ? jsc - jj : jj - jec;
+          const double sg = (xo_w == yo_s) ? -1.0 : 1.0;
+          const int si = xo_w ? isc + b - 1 : iec + 1 - b;
+          const int sjj = yo_s ? jsc - a : jec + 1 + a;
+          return sg * vc_raw(si, sjj);
+        }
+      }
+      return uc_raw(ii, jj);
+    };
+    const double ucm = uc_at(i, j - 1), uc0 = uc_at(i, j), vcm = vc_at(i - 1, j), vc0 = vc_at(i, j);
+    double d = ucm - uc0 + vcm - vc0;
+    const bool ci = (W && i == isc) || (E && i == iec + 1);
+    if (ci && S && j == jsc) d = d - ucm;
+    if (ci && N && j == jec + 1) d = d + uc0;
+    dnew[O3(s, i, j, k)] = d * m.rarea_c[O2(s, i, j)];
+  });
+}
+
+void divergence_damping(fv3_ctx *ctx, cudaStream_t st, const double *u, const double *v, const double *va, double *vort_b,
+                        const double *ua, double *divg_d, const double *vc, const double *uc, double *delpc, double *ke,
+                        const double *vort_a, double dt, const fv3_dsw_cols *c) {
+  const fv3_geom g = ctx->g;
+  const fv3_grid m = ctx->m;
+  const Ix x = make_ix(g);
+  const int isc = x.isc, iec = x.iec, jsc = x.jsc, jec = x.jec, sj = g.sj, nz = g.nz;
+  const int k0 = c->nonzero_nord_k;
+  const int nord = c->nonzero_nord;
+  const double da_min_c = ctx->c.da_min_c, dddmp = ctx->c.dddmp;
+  const double *d2_bg = c->d2_divg;
+  if (k0 > 0) {
+    // levels [0, k0): second-order damping (divergence_damping.py:21-118,504-548)
+    fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, 0, k0, FV_LAMBDA(int s, int i, int j, int k) {
+      const bool W = fv3::on_west(g, s), E = fv3::on_east(g, s), S = fv3::on_south(g, s), N = fv3::on_north(g, s);
+      auto ucd = [&](int ii, int jj) {  // u_contra * dyc at (x centre, y interface)
+        const int64_t o = O3(s, ii, jj, k), o2 = O2(s, ii, jj);
+        double uco;
+        if ((S && jj == jsc) || (N && jj == jec + 1))
+          uco = vc[o] > 0 ? u[o] * m.sin_sg4[o2 - sj] : u[o] * m.sin_sg2[o2];
+        else
+          uco = (u[o] - 0.5 * (va[o - sj] + va[o]) * m.cosa_v[o2]) * m.sina_v[o2];
+        return uco * m.dyc[o2];
+      };
+      auto vcd = [&](int ii, int jj) {
+        const int64_t o = O3(s, ii, jj, k), o2 = O2(s, ii, jj);
+        double vco;
+        if ((W && ii == isc) || (E && ii == iec + 1))
+          vco = uc[o] > 0 ? v[o] * m.sin_sg3[o2 - 1] : v[o] * m.sin_sg1[o2];
+        else
+          vco = (v[o] - 0.5 * (ua[o - 1] + ua[o]) * m.cosa_u[o2]) * m.sina_u[o2];
+        return vco * m.dxc[o2];
+      };
+      const double vm = vcd(i, j - 1), v0 = vcd(i, j), um = ucd(i - 1, j), u0 = ucd(i, j);
+      double d = vm - v0 + um - u0;
+      const bool ci = (W && i == isc) || (E && i == iec + 1);
+      if (ci && S && j == jsc) d = d - vm;
+      if (ci && N && j == jec + 1) d = d + v0;
+      const int64_t o = O3(s, i, j, k);
+      d = m.rarea_c[O2(s, i, j)] * d;
+      delpc[o] = d;
+      const double delpcdt = d * dt;
+      const double damp = da_min_c * fv3::dmax(d2_bg[k], fv3::dmin(0.2, dddmp * fabs(delpcdt)));
+      const double vo = damp * d;
+      vort_b[o] = vo;
+      ke[o] = ke[o] + vo;
+    });
+  }
+  // levels [k0, nz): delpc <- divg_d, then nord Laplacian iterations on divg_d
+  fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, k0, nz, FV_LAMBDA(int s, int i, int j, int k) {
+    const int64_t o = O3(s, i, j, k);
+    delpc[o] = divg_d[o];
+  });
+  double *tmp = fv3::scratch_field(ctx, 7);
+  double *bufs[2] = {divg_d, tmp};
+  int cur = 0;
+  for (int n = 0; n < nord; ++n) {
+    const int nt = nord - (n + 1);
+    const bool fillc = (n + 1 != nord);
+    divg_iteration(ctx, st, bufs[cur], bufs[1 - cur], nt, fillc, k0);
+    cur = 1 - cur;
+  }
+  if (cur == 1) {  // result sits in the scratch buffer: bring it back over the final (compute) domain
+    fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, k0, nz, FV_LAMBDA(int s, int i, int j, int k) {
+      const int64_t o = O3(s, i, j, k);
+      divg_d[o] = tmp[o];
+    });
+  }
+  const double absdt = fabs(dt);
+  double dd8 = 1.0;
+  {
+    const double base = da_min_c * ctx->c.d4_bg;
+    for (int n = 0; n < nord + 1; ++n) dd8 *= base;
+    dd8 = pow(base, (double)(nord + 1));
+  }
+  // a2b_ord4 of the relative vorticity + Smagorinsky-type diffusion + high-order damping
+  // (divergence_damping.py:590-632)
+  fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, k0, nz, FV_LAMBDA(int s, int i, int j, int k) {
+    const int64_t o = O3(s, i, j, k);
+    double vo;
+    if (dddmp < 1e-5) {
+      vo = 0.0;
+    } else {
+      auto q = [&](int ii, int jj) { return vort_a[O3(s, ii, jj, k)]; };
+      const double vb = fv3::a2b_point(g, m, s, q, i, j);
+      const double dp = delpc[o];
+      vo = absdt * sqrt(dp * dp + vb * vb);
+    }
+    const double damp = da_min_c * fv3::dmax(d2_bg[k], fv3::dmin(0.2, dddmp * fabs(vo)));
+    vo = damp * delpc[o] + dd8 * divg_d[o];
+    vort_b[o] = vo;
+    ke[o] = ke[o] + vo;
+  });
+}
+
+// D-grid wind advected along its own direction to a cell corner: advect_u_along_x / advect_v_along_y
+// (xtp_u.py:9-91, ytp_v.py), iord < 8.  q(n): wind at index n along the sweep; dxe(n): dx (or dy) for the edge
+// formula of compute_al; zero(n): bl = br = 0 at the cells next to a cube corner (xtp_u.py:39-47)
+template <class Q, class DXE, class Z>
+FV_HD double advect_along(int mord, Q q, DXE dxe, Z zero, double ub, double cfl, int i, const fv3::Edge1D &e) {
+  const double al0 = fv3::ppm_al_lt8(q, dxe, i - 1, e), al1 = fv3::ppm_al_lt8(q, dxe, i, e), al2 = fv3::ppm_al_lt8(q, dxe, i + 1, e);
+  const double ql = q(i - 1), qr = q(i);
+  double bl_l = al0 - ql, br_l = al1 - ql, bl_r = al1 - qr, br_r = al2 - qr;
+  if (zero(i - 1)) bl_l = br_l = 0.0;
+  if (zero(i)) bl_r = br_r = 0.0;
+  const double b0_l = bl_l + br_l, b0_r = bl_r + br_r;
+  const double fx0 = fv3::ppm_fx1(cfl, br_l, b0_l, bl_r, b0_r);
+  bool s_l, s_r;
+  if (mord == 5) {
+    s_l = bl_l * br_l < 0;
+    s_r = bl_r * br_r < 0;
+  } else {
+    s_l = (3.0 * fabs(b0_l)) < fabs(bl_l - br_l);
+    s_r = (3.0 * fabs(b0_r)) < fabs(bl_r - br_r);
+  }
+  const double mask = (s_l || s_r) ? 1.0 : 0.0;
+  return ub > 0.0 ? ql + fx0 * mask : qr + fx0 * mask;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fv3_a2b_ord4(fv3_ctx *ctx, const double *qin, double *qout, int kstart, int nk, void *stream) {
+  a2b_ord4_launch(ctx, (cudaStream_t)stream, qin, qout, kstart, kstart + nk);
+  return fv3::check_launch("fv3_a2b_ord4");
+}
+
+int fv3_divergence_damping(fv3_ctx *ctx, const double *u, const double *v, const double *va, double *damped_rel_vort_bgrid,
+                           const double *ua, double *divg_d, const double *vc, const double *uc, double *delpc, double *ke,
+                           const double *rel_vort_agrid, double dt, const fv3_dsw_cols *cols, void *stream) {
+  if (cols->nonzero_nord > 3) {
+    fv3::set_error("fv3_divergence_damping: nord > 3");
+    return -1;
+  }
+  divergence_damping(ctx, (cudaStream_t)stream, u, v, va, damped_rel_vort_bgrid, ua, divg_d, vc, uc, delpc, ke,
+                     rel_vort_agrid, dt, cols);
+  return fv3::check_launch("fv3_divergence_damping");
+}
+
+int fv3_d_sw(fv3_ctx *ctx, double *delpc, double *delp, double *pt, double *u, double *v, double *w, double *uc,
+             double *vc, const double *ua, const double *va, double *divgd, double *mfx, double *mfy, double *cx,
+             double *cy, double *crx, double *cry, double *xfx, double *yfx, double *q_con, const double *zh,
+             double *heat_source, double *diss_est, double dt, const fv3_dsw_cols *c, void *stream) {
+  (void)zh;
+  const fv3_geom g = ctx->g;
+  const fv3_grid m = ctx->m;
+  const fv3_config cfg = ctx->c;
+  cudaStream_t st = (cudaStream_t)stream;
+  const Ix x = make_ix(g);
+  const int isc = x.isc, iec = x.iec, jsc = x.jsc, jec = x.jec, ied = x.ied, jed = x.jed, sj = g.sj, nz = g.nz;
+  int rc;
+  double *ucc = fv3::scratch_field(ctx, 16), *vcc = fv3::scratch_field(ctx, 17);
+  double *fx = fv3::scratch_field(ctx, 18), *fy = fv3::scratch_field(ctx, 19);
+  double *fx2 = fv3::scratch_field(ctx, 20), *fy2 = fv3::scratch_field(ctx, 21);
+  double *dw = fv3::scratch_field(ctx, 22), *heat_s = fv3::scratch_field(ctx, 23);
+  double *gxw = fv3::scratch_field(ctx, 24), *gyw = fv3::scratch_field(ctx, 25);
+  double *gxq = fv3::scratch_field(ctx, 26), *gyq = fv3::scratch_field(ctx, 27);
+  double *gxp = fv3::scratch_field(ctx, 28), *gyp = fv3::scratch_field(ctx, 29);
+  double *ke = fv3::scratch_field(ctx, 30), *vort_a = fv3::scratch_field(ctx, 31);
+  double *vort_b = fv3::scratch_field(ctx, 32), *abs_vort = fv3::scratch_field(ctx, 33);
+  double *ut = fv3::scratch_field(ctx, 34), *vt = fv3::scratch_field(ctx, 35);
+  const double *damp_w = c->damp_w, *ke_bg = c->ke_bg, *d_con = c->d_con, *damp_vt = c->damp_vt;
+
+  if ((rc = fv3_fv_prep(ctx, uc, vc, crx, cry, xfx, yfx, ucc, vcc, dt, stream))) return rc;
+  // delp transport fluxes (mass fluxes) with del-n damping (d_sw.py:967-975)
+  if ((rc = fv3_fvtp2d(ctx, delp, crx, cry, xfx, yfx, fx, fy, nullptr, nullptr, nullptr, cfg.hord_dp, c->nord_v,
+                       c->dn_damp_vt, c->nmax_v, nz, stream)))
+    return rc;
+  // flux_capacitor (d_sw.py:29-50) on the full domain
+  fv3::launch3d(ctx, st, 0, ied + 1, 0, jed + 1, 0, nz, FV_LAMBDA(int s, int i, int j, int k) {
+    const int64_t o = O3(s, i, j, k);
+    cx[o] = cx[o] + crx[o];
+    cy[o] = cy[o] + cry[o];
+    mfx[o] = mfx[o] + fx[o];
+    mfy[o] = mfy[o] + fy[o];
+  });
+  // w: del-n fluxes of damp_w * w, heat dissipation (d_sw.py:53-103)
+  if ((rc = fv3_delnflux_nosg(ctx, w, fx2, fy2, c->dn_damp_w_c, c->nord_w, c->nmax_w, nz, stream))) return rc;
+  fv3::launch3d(ctx, st, isc, iec + 1, jsc, jec + 1, 0, nz, FV_LAMBDA(int s, int i, int j, int k) {
+    const int64_t o = O3(s, i, j, k);
+    double hs = 0.0;
+    if (damp_w[k] > 1e-5) {
+      const double dd8 = ke_bg[k] * fabs(dt);
+      const double d = (fx2[o] - fx2[o + 1] + fy2[o] - fy2[o + sj]) * m.rarea[O2(s, i, j)];
+      dw[o] = d;
+      hs = dd8 - d * (w[o] + 0.5 * d);
+    }
+    heat_s[o] = hs;
+    diss_est[o] = hs;
+  });
+  if ((rc = fv3_fvtp2d(ctx, w, crx, cry, xfx, yfx, gxw, gyw, fx, fy, nullptr, cfg.hord_vt, nullptr, nullptr, 0, nz, stream))) return rc;
+  if ((rc = fv3_fvtp2d(ctx, q_con, crx, cry, xfx, yfx, gxq, gyq, fx, fy, delp, cfg.hord_dp, c->nord_t, c->dn_damp_t, c->nmax_t, nz, stream))) return rc;
+  if ((rc = fv3_fvtp2d(ctx, pt, crx, cry, xfx, yfx, gxp, gyp, fx, fy, delp, cfg.hord_tm, c->nord_v, c->dn_damp_vt, c->nmax_v, nz, stream))) return rc;
+  // apply_fluxes (w, q_con), apply_pt_delp_fluxes, adjust_w_and_qcon (d_sw.py:106-160,331-346) on the compute domain
+  fv3::launch3d(ctx, st, isc, iec + 1, jsc, jec + 1, 0, nz, FV_LAMBDA(int s, int i, int j, int k) {
+    const int64_t o = O3(s, i, j, k);
+    const double ra = m.rarea[O2(s, i, j)];
+    const double dp0 = delp[o];
+    double wv = w[o] * dp0 + (gxw[o] - gxw[o + 1] + gyw[o] - gyw[o + sj]) * ra;
+    double qc = q_con[o] * dp0 + (gxq[o] - gxq[o + 1] + gyq[o] - gyq[o + sj]) * ra;
+    double ptv = pt[o] * dp0 + (gxp[o] - gxp[o + 1] + gyp[o] - gyp[o + sj]) * ra;
+    const double dp1 = dp0 + (fx[o] - fx[o + 1] + fy[o] - fy[o + sj]) * ra;
+    ptv = ptv / dp1;
+    wv = wv / dp1;
+    if (damp_w[k] > 1e-5) wv = wv + dw[o];
+    qc = qc / dp1;
+    delp[o] = dp1;
+    pt[o] = ptv;
+    w[o] = wv;
+    q_con[o] = qc;
+  });
+  // kinetic energy on cell corners (d_sw.py:204-298)
+  const int mord = cfg.hord_mt < 0 ? -cfg.hord_mt : cfg.hord_mt;
+  if (mord >= 8) {
+    fv3::set_error("fv3_d_sw: hord_mt >= 8 is not implemented");
+    return -1;
+  }
+  fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, 0, nz, FV_LAMBDA(int s, int i, int j, int k) {
+    const bool W = fv3::on_west(g, s), E = fv3::on_east(g, s), S = fv3::on_south(g, s), N = fv3::on_north(g, s);
+    const int64_t o = O3(s, i, j, k), o2 = O2(s, i, j);
+    const bool ie_ = (W && i == isc) || (E && i == iec + 1), je_ = (S && j == jsc) || (N && j == jec + 1);
+    const double ub_cov = 0.5 * (uc[o - sj] + uc[o]), vb_cov = 0.5 * (vc[o - 1] + vc[o]);
+    double ub = (ub_cov - vb_cov * m.cosa[o2]) * m.rsina[o2];
+    double vb = (vb_cov - ub_cov * m.cosa[o2]) * m.rsina[o2];
+    if (je_) ub = 0.25 * (-ucc[o - 2 * sj] + 3.0 * (ucc[o - sj] + ucc[o]) - ucc[o + sj]);
+    if (ie_) ub = 0.5 * (ucc[o - sj] + ucc[o]);
+    if (ie_) vb = 0.25 * (-vcc[o - 2] + 3.0 * (vcc[o - 1] + vcc[o]) - vcc[o + 1]);
+    if (je_) vb = 0.5 * (vcc[o - 1] + vcc[o]);
+    double kev;
+    if (ie_ && je_) {
+      // corner_ke (d_sw.py:258-283)
+      int io1, jo1, io2;
+      double vsign;
+      if (i == isc && j == jsc) { io1 = 0; jo1 = 0; io2 = -1; vsign = 1; }
+      else if (i != isc && j == jsc) { io1 = -1; jo1 = 0; io2 = 0; vsign = -1; }
+      else if (i != isc && j != jsc) { io1 = -1; jo1 = -1; io2 = 0; vsign = 1; }
+      else { io1 = 0; jo1 = -1; io2 = -1; vsign = -1; }
+      const double dt6 = dt / 6.0;
+      const double u0 = u[o], um = u[o - 1], v0 = v[o], vm = v[o - sj];
+      const double ut0 = ucc[o], utm = ucc[o - sj], vt0 = vcc[o], vtm = vcc[o - 1];
+      kev = dt6 * ((ut0 + utm) * ((io1 + 1) * u0 - (io1 * um)) + (vt0 + vtm) * ((jo1 + 1) * v0 - (jo1 * vm)) +
+                   (((jo1 + 1) * ut0 - (jo1 * utm)) + vsign * ((io1 + 1) * vt0 - (io1 * vtm))) * ((io2 + 1) * u0 - (io2 * um)));
+    } else {
+      const fv3::Edge1D ex{W, E, isc, iec}, ey{S, N, jsc, jec};
+      auto qu = [&](int ii) { return u[O3(s, ii, j, k)]; };
+      auto dxe = [&](int ii) { return m.dx[O2(s, ii, j)]; };
+      auto zx = [&](int ii) { return je_ && ((W && (ii == isc - 1 || ii == isc)) || (E && (ii == iec || ii == iec + 1))); };
+      const double cflx = ub > 0 ? ub * dt * m.rdx[o2 - 1] : ub * dt * m.rdx[o2];
+      const double adv_u = advect_along(mord, qu, dxe, zx, ub, cflx, i, ex);
+      auto qv = [&](int jj) { return v[O3(s, i, jj, k)]; };
+      auto dye = [&](int jj) { return m.dy[O2(s, i, jj)]; };
+      auto zy = [&](int jj) { return ie_ && ((S && (jj == jsc - 1 || jj == jsc)) || (N && (jj == jec || jj == jec + 1))); };
+      const double cfly = vb > 0 ? vb * dt * m.rdy[o2 - sj] : vb * dt * m.rdy[o2];
+      const double adv_v = advect_along(mord, qv, dye, zy, vb, cfly, j, ey);
+      kev = 0.5 * dt * (ub * adv_u + vb * adv_v);
+    }
+    ke[o] = kev;
+  });
+  // relative vorticity on the A grid, full domain (d_sw.py:301-328)
+  fv3::launch3d(ctx, st, 0, ied + 1, 0, jed + 1, 0, nz, FV_LAMBDA(int s, int i, int j, int k) {
+    const int64_t o = O3(s, i, j, k), o2 = O2(s, i, j);
+    const double rdy_tmp = m.rarea[o2] * m.dx[o2], rdx_tmp = m.rarea[o2] * m.dy[o2];
+    vort_a[o] = (u[o] - u[o + sj] * m.dx[o2 + sj] / m.dx[o2]) * rdy_tmp + (v[o + 1] * m.dy[o2 + 1] / m.dy[o2] - v[o]) * rdx_tmp;
+  });
+  divergence_damping(ctx, st, u, v, va, vort_b, ua, divgd, vc, uc, delpc, ke, vort_a, dt, c);
+  // absolute vorticity and its transport (d_sw.py:1131-1147)
+  fv3::launch3d(ctx, st, 0, ied + 1, 0, jed + 1, 0, nz, FV_LAMBDA(int s, int i, int j, int k) {
+    const int64_t o = O3(s, i, j, k);
+    abs_vort[o] = vort_a[o] + m.f0[O2(s, i, j)];
+  });
+  if ((rc = fv3_fvtp2d(ctx, abs_vort, crx, cry, xfx, yfx, fx, fy, nullptr, nullptr, nullptr, cfg.hord_vt, nullptr, nullptr, 0, nz, stream))) return rc;
+  // u_and_v_from_ke (d_sw.py:439-477)
+  fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, 0, nz, FV_LAMBDA(int s, int i, int j, int k) {
+    const int64_t o = O3(s, i, j, k), o2 = O2(s, i, j);
+    if (i <= iec) u[o] = u[o] * m.dx[o2] + ke[o] - ke[o + 1] + fy[o];
+    if (j <= jec) v[o] = v[o] * m.dy[o2] + ke[o] - ke[o + sj] - fx[o];
+  });
+  // del-n damping fluxes of the relative vorticity (d_sw.py:1160-1166)
+  if ((rc = fv3_delnflux_nosg(ctx, vort_a, ut, vt, c->dn_damp_vt_c, c->nord_v, c->nmax_v, nz, stream))) return rc;
+  // vort_differencing + heat_source_from_vorticity_damping (d_sw.py:349-577) on the compute domain
+  const double d_con_cfg = cfg.d_con;
+  fv3::launch3d(ctx, st, isc, iec + 1, jsc, jec + 1, 0, nz, FV_LAMBDA(int s, int i, int j, int k) {
+    const bool dc = d_con[k] > DCON_THRESHOLD;
+    auto ubt = [&](int ii, int jj) {  // defined on [isc..iec] x [jsc..jec+1]
+      const int64_t p = O3(s, ii, jj, k);
+      const double vxd = dc ? vort_b[p] - vort_b[p + 1] : 0.0;
+      return (vxd + vt[p]) * m.rdx[O2(s, ii, jj)];
+    };
+    auto vbt = [&](int ii, int jj) {  // defined on [isc..iec+1] x [jsc..jec]
+      const int64_t p = O3(s, ii, jj, k);
+      const double vyd = dc ? vort_b[p] - vort_b[p + sj] : 0.0;
+      return (vyd - ut[p]) * m.rdy[O2(s, ii, jj)];
+    };
+    const int64_t o = O3(s, i, j, k), o2 = O2(s, i, j);
+    double hs = heat_s[o];
+    if (dc) {
+      const double ub0 = ubt(i, j), ub1 = ubt(i, j + 1), vb0 = vbt(i, j), vb1 = vbt(i + 1, j);
+      const double fy0 = u[o] * m.rdx[o2], fy1 = u[o + sj] * m.rdx[o2 + sj];
+      const double fx0 = v[o] * m.rdy[o2], fx1 = v[o + 1] * m.rdy[o2 + 1];
+      const double gy0 = fy0 * ub0, gy1 = fy1 * ub1, gx0 = fx0 * vb0, gx1 = fx1 * vb1;
+      const double u2 = fy0 + fy1, du2 = ub0 + ub1, v2 = fx0 + fx1, dv2 = vb0 + vb1;
+      const double dampterm = m.rsin2[o2] * 0.25 *
+                              ((ub0 * ub0 + ub1 * ub1 + vb0 * vb0 + vb1 * vb1) + 2.0 * (gy0 + gy1 + gx0 + gx1) -
+                               m.cosa_s[o2] * (u2 * dv2 + v2 * du2 + du2 * dv2));
+      hs = delp[o] * (hs - d_con[k] * dampterm);
+    }
+    if (d_con_cfg > DCON_THRESHOLD) heat_source[o] = heat_source[o] + hs;
+  });
+  // update_u_and_v (d_sw.py:582-608)
+  fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, 0, nz, FV_LAMBDA(int s, int i, int j, int k) {
+    if (!(damp_vt[k] > 1e-5)) return;
+    const int64_t o = O3(s, i, j, k);
+    if (i <= iec) u[o] = u[o] + vt[o];
+    if (j <= jec) v[o] = v[o] - ut[o];
+  });
+  return fv3::check_launch("fv3_d_sw");
+}
+
+}  // extern "C"

@@ -1,10 +1,42 @@
 """Native context shared by all stage objects of one process: geometry, config, metric-term pointers, scratch."""
 import ctypes
 
+import numpy as np
+
 import torch
 
 from .. import _lib
 from ..util.grid.helper import DampingCoefficients, GridData
+
+
+def _great_circle_dist(p1a, p1b, p2a, p2b):
+    """a2b_ord4.great_circle_dist (a2b_ord4.py:37-41), evaluated with numpy on the host."""
+    tb = np.sin((p1b - p2b) / 2.0) ** 2.0
+    ta = np.sin((p1a - p2a) / 2.0) ** 2.0
+    return np.arcsin(np.sqrt(tb + np.cos(p1b) * np.cos(p2b) * ta)) * 2.0
+
+
+def a2b_corner_weights(grid_data, g) -> np.ndarray:
+    """Weights x1 / (x2 - x1) of extrap_corner (a2b_ord4.py:43-56) for the 4 corner points of every local
+    subdomain and the 3 arms (into the tile, across the x edge, across the y edge)."""
+    lon, lat = grid_data.host("lon"), grid_data.host("lat")
+    lona, lata = grid_data.host("lon_agrid"), grid_data.host("lat_agrid")
+    h, nx, ny = g.halo, g.nx, g.ny
+    out = np.zeros((g.n_sub, 4, 3))
+    for s in range(g.n_sub):
+        for c in range(4):
+            west, south = (c % 2 == 0), (c < 2)
+            i = h if west else h + nx
+            j = h if south else h + ny
+            di, dj = (1 if west else -1), (1 if south else -1)
+            i0, j0 = (i if west else i - 1), (j if south else j - 1)
+            arms = [((i0, j0), (i0 + di, j0 + dj)), ((i0 - di, j0), (i0 - 2 * di, j0 + dj)),
+                    ((i0, j0 - dj), (i0 + di, j0 - 2 * dj))]
+            for a, (p1, p2) in enumerate(arms):
+                x1 = _great_circle_dist(lona[s][p1], lata[s][p1], lon[s, i, j], lat[s, i, j])
+                x2 = _great_circle_dist(lona[s][p2], lata[s][p2], lon[s, i, j], lat[s, i, j])
+                out[s, c, a] = x1 / (x2 - x1)
+    return out
 
 
 class Runtime:
@@ -47,6 +79,8 @@ class Runtime:
             t = q.data if hasattr(q, "data") and not isinstance(q, torch.Tensor) else q
             self._keep.append(t)
             setattr(grid, name, t.data_ptr())
+        self._a2b_w = torch.as_tensor(a2b_corner_weights(grid_data, g)).to(self.device)
+        grid.a2b_w = self._a2b_w.data_ptr()
         n_scratch = self.lib.fv3_scratch_fields()
         self.scratch = torch.zeros(n_scratch * g.ss * g.n_sub, dtype=torch.float64, device=self.device)
         self.c_geom = comm.c_geom

@@ -223,3 +223,65 @@ def _make_delnflux(n, nord_name):
 
 _make_delnflux(0, "nord_w")
 _make_delnflux(1, "nord_v")
+
+
+# ---------------------------------------------------------------------------------------------
+CORNERS = (slice(3, 3 + NX + 1), slice(3, 3 + NX + 1))
+COMPUTE = (slice(3, 3 + NX), slice(3, 3 + NX))
+
+
+def _dsw_cols(rt):
+    from pace_b200.fv3core._config import baroclinic_config
+    from pace_b200.fv3core.stencils.d_sw import ColumnNamelist
+
+    return ColumnNamelist(rt, baroclinic_config(NX).d_grid_shallow_water, rt.damping)
+
+
+def _n_a2b(kstart):
+    def native(sf, qf, rt, q, d):
+        rt.call("fv3_a2b_ord4", q["qin"].ptr, q["qout"].ptr, kstart, NZ - kstart)
+
+    return native
+
+
+def _o_todo(ix, g, a):
+    import pytest
+
+    pytest.skip("numpy oracle for this stage not written yet (native kernels are pinned on the reference golden)")
+
+
+register(StageSpec("a2b_ord4_0", "A2B_Ord4#0", ("qout",), _o_todo, _n_a2b(3), regions={"qout": CORNERS}, tol=1e-13))
+
+
+def _n_divdamp(sf, qf, rt, q, d):
+    cols = _dsw_cols(rt)
+    rt.call("fv3_divergence_damping", q["u"].ptr, q["v"].ptr, q["va"].ptr, q["damped_rel_vort_bgrid"].ptr, q["ua"].ptr,
+            q["divg_d"].ptr, q["vc"].ptr, q["uc"].ptr, q["delpc"].ptr, q["ke"].ptr, q["rel_vort_agrid"].ptr, f(d, "dt"),
+            cols.ref)
+
+
+register(StageSpec("divergence_damping", "DivergenceDamping#0", ("damped_rel_vort_bgrid", "ke", "delpc", "divg_d"), _o_todo,
+                   _n_divdamp, regions={n: CORNERS for n in ("damped_rel_vort_bgrid", "ke", "delpc", "divg_d")}, tol=1e-13,
+                   check_untouched=False))
+
+
+def _n_dsw(sf, qf, rt, q, d):
+    from pace_b200.fv3core._config import baroclinic_config
+    from pace_b200.fv3core.stencils.d_sw import DGridShallowWaterLagrangianDynamics
+
+    cfg = baroclinic_config(NX).d_grid_shallow_water
+    dsw = DGridShallowWaterLagrangianDynamics(sf, qf, rt.grid_data, rt.damping, _dsw_cols(rt), False, False, cfg)
+    dsw(*[q[n] for n in ("delpc", "delp", "pt", "u", "v", "w", "uc", "vc", "ua", "va", "divgd", "mfx", "mfy", "cx", "cy",
+                         "crx", "cry", "xfx", "yfx", "q_con", "zh", "heat_source", "diss_est")], f(d, "dt"))
+
+
+_XI = (slice(3, 3 + NX + 1), slice(3, 3 + NX))      # x-interface fields on the compute rows
+_YI = (slice(3, 3 + NX), slice(3, 3 + NX + 1))
+register(StageSpec(
+    "d_sw", "D_SW#0",
+    ("delp", "pt", "w", "q_con", "u", "v", "mfx", "mfy", "cx", "cy", "crx", "cry", "xfx", "yfx", "heat_source", "diss_est"),
+    _o_todo, _n_dsw, tol=1e-12, check_untouched=False,
+    regions={"delp": COMPUTE, "pt": COMPUTE, "w": COMPUTE, "q_con": COMPUTE, "u": _YI, "v": _XI, "mfx": _XI, "mfy": _YI,
+             "cx": _XI, "cy": _YI, "crx": (slice(3, 3 + NX + 1), slice(None)), "cry": (slice(None), slice(3, 3 + NX + 1)),
+             "xfx": (slice(3, 3 + NX + 1), slice(None)), "yfx": (slice(None), slice(3, 3 + NX + 1)),
+             "heat_source": COMPUTE, "diss_est": COMPUTE}))
