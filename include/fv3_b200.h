@@ -163,6 +163,34 @@ int fv3_d_sw(fv3_ctx *ctx, double *delpc, double *delp, double *pt, double *u, d
              double *cy, double *crx, double *cry, double *xfx, double *yfx, double *q_con, const double *zh,
              double *heat_source, double *diss_est, double dt, const fv3_dsw_cols *cols, void *stream);
 
+/* ---- UpdateHeightOnDGrid.__call__ (updatedzd.py:283-356).  gk/beta/gamma: cubic-spline constants
+ *      (updatedzd.py:129-154); damp_col: the RAW damp_vt column padded with 0 at level nz (updatedzd.py:337-343);
+ *      nord_col: nord_v column; all device double[nz+1]. */
+int fv3_update_dz_d(fv3_ctx *ctx, const double *surface_height, double *height, const double *crx, const double *cry,
+                    const double *xfx, const double *yfx, double *ws, double dt, const double *gk, const double *beta,
+                    const double *gamma, const double *damp_col, const double *nord_col, int nmax, void *stream);
+
+/* ---- NonhydrostaticVerticalSolver.__call__ (riem_solver3.py:207-321), same argument order */
+int fv3_riem_solver3(fv3_ctx *ctx, int last_call, double dt, const double *cappa, double ptop, const double *zs,
+                     const double *ws, double *delz, const double *q_con, const double *delp, const double *pt,
+                     double *zh, double *pe, double *ppe, double *pk3, double *pk, double *peln, double *w,
+                     void *stream);
+/* ---- edge_pe (pe_halo.py:6-34) and PK3Halo.__call__ (pk3_halo.py:11-69) */
+int fv3_edge_pe(fv3_ctx *ctx, double *pe, const double *delp, double ptop, void *stream);
+int fv3_pk3_halo(fv3_ctx *ctx, double *pk3, const double *delp, double ptop, double akap, void *stream);
+/* ---- NonHydrostaticPressureGradient.__call__ (nh_p_grad.py:190-255); pp, gz, pk3 are replaced by their
+ *      B-grid (cell-corner) values as in the reference */
+int fv3_nh_p_grad(fv3_ctx *ctx, double *u, double *v, double *pp, double *gz, double *pk3, const double *delp,
+                  double dt, double ptop, double akap, void *stream);
+/* ---- RayleighDamping.__call__ (ray_fast.py:184-206); rf column and the level counts are host-computed */
+int fv3_ray_fast(fv3_ctx *ctx, double *u, double *v, double *w, const double *rf, int n_rf, int n_nudge, double p_ref,
+                 void *stream);
+/* ---- HyperdiffusionDamping.__call__ (del2cubed.py:165-194) */
+int fv3_del2cubed(fv3_ctx *ctx, double *qdel, double cd, int nmax, int nk, void *stream);
+/* ---- apply_diffusive_heating (temperature_adjust.py:8-43) on the first nk levels */
+int fv3_apply_diffusive_heating(fv3_ctx *ctx, const double *delp, const double *delz, const double *cappa,
+                                const double *heat_source, double *pt, double delt_time_factor, int nk, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

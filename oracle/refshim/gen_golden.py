@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--out", required=True)
     ap.add_argument("--n-split", type=int, default=1)
     ap.add_argument("--k-split", type=int, default=1)
+    ap.add_argument("--capture-step", type=int, default=0, help="0-based index of the step whose stages are captured")
     args = ap.parse_args()
 
     from oracle.refshim import runner
@@ -34,12 +35,12 @@ def main():
     t0 = time.time()
     ctxs, cap = runner.run(
         args.nx, (args.layout, args.layout), nsteps=args.nsteps, capture_ranks=tuple(args.capture_ranks),
-        config_overrides=dict(n_split=args.n_split, k_split=args.k_split),
+        config_overrides=dict(n_split=args.n_split, k_split=args.k_split), capture_step=args.capture_step,
     )
     for ctx in ctxs:
         r = ctx["rank"]
         np.savez(os.path.join(args.out, f"grid_rank{r}.npz"), **runner.grid_arrays(ctx))
-        np.savez(os.path.join(args.out, f"state0_rank{r}.npz"), **ctx["state0"])
+        np.savez(os.path.join(args.out, f"state0_rank{r}.npz"), **ctx.get("state_before_capture", ctx["state0"]))
         np.savez(os.path.join(args.out, f"state1_rank{r}.npz"), **runner.state_arrays(ctx["state"]))
     for r, stages in cap.data.items():
         d = os.path.join(args.out, f"stage_rank{r}")
@@ -48,7 +49,7 @@ def main():
             flat = {f"in.{k}": v for k, v in rec["in"].items()}
             flat.update({f"out.{k}": v for k, v in rec["out"].items()})
             np.savez(os.path.join(d, key + ".npz"), **flat)
-    meta = dict(nx=args.nx, layout=args.layout, nsteps=args.nsteps, n_split=args.n_split, k_split=args.k_split,
+    meta = dict(capture_step=args.capture_step, nx=args.nx, layout=args.layout, nsteps=args.nsteps, n_split=args.n_split, k_split=args.k_split,
                 timing=ctxs[0].get("timing"), wall=time.time() - t0, config=runner.C12_CONFIG,
                 reference="ai2cm/pace @ /root/reference, numpy backend via oracle/refshim")
     with open(os.path.join(args.out, "meta.json"), "w") as f:

@@ -311,7 +311,7 @@ def state_arrays(state):
 
 
 def run(nx, layout=(1, 1), nsteps=1, capture_ranks=(0,), stages=None, config_overrides=None, build_only=False,
-        on_built=None, verbose=True):
+        on_built=None, verbose=True, capture_step=0):
     """Run `nsteps` of the reference dycore on 6*layout^2 thread-ranks.
 
     Returns (contexts, capture).  contexts[r] holds grid_data/state/dycore of rank r plus
@@ -336,8 +336,12 @@ def run(nx, layout=(1, 1), nsteps=1, capture_ranks=(0,), stages=None, config_ove
             if on_built is not None:
                 on_built(ctx)
             ctx["timing"] = []
-            for _ in range(nsteps):
+            for step in range(nsteps):
                 world.barrier.wait()
+                if rank in capture.ranks or rank == 0:
+                    capture.enabled = step == capture_step
+                if step == capture_step:
+                    ctx["state_before_capture"] = state_arrays(ctx["state"])
                 t0 = time.time()
                 ctx["dycore"].step_dynamics(ctx["state"], pace.util.NullTimer())
                 world.barrier.wait()

@@ -1,0 +1,179 @@
+// Non-hydrostatic pressure-gradient update of the D-grid winds and the remaining end-of-substep stencils.
+//   fv3_nh_p_grad               <- NonHydrostaticPressureGradient.__call__ (nh_p_grad.py:190-255)
+//   fv3_ray_fast                <- RayleighDamping.__call__ (ray_fast.py:184-206)
+//   fv3_del2cubed               <- HyperdiffusionDamping.__call__ (del2cubed.py:165-194)
+//   fv3_apply_diffusive_heating <- apply_diffusive_heating (temperature_adjust.py:8-43)
+#include "a2b.h"
+#include "common.h"
+#include "ppm.h"
+
+extern "C" {
+
+int fv3_nh_p_grad(fv3_ctx *ctx, double *u, double *v, double *pp, double *gz, double *pk3, const double *delp,
+                  double dt, double ptop, double akap, void *stream) {
+  const fv3_geom g = ctx->g;
+  const fv3_grid m = ctx->m;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int h = g.halo, nz = g.nz, sj = g.sj;
+  const int isc = h, iec = h + g.nx - 1, jsc = h, jec = h + g.ny - 1;
+  const int64_t sk = g.sk;
+  double *ppb = fv3::scratch_field(ctx, 16), *pk3b = fv3::scratch_field(ctx, 17), *gzb = fv3::scratch_field(ctx, 18);
+  double *wk1 = fv3::scratch_field(ctx, 19);
+  const double top_value = pow(ptop, akap);  // host libm, as `ptop ** akap` in the reference (:219)
+  // four A->B interpolations (nh_p_grad.py:221-224) + set_k0 (:11-20)
+  fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, 0, nz + 1, FV_LAMBDA(int s, int i, int j, int k) {
+    const int64_t o = O3(s, i, j, k);
+    auto qgz = [&](int ii, int jj) { return gz[O3(s, ii, jj, k)]; };
+    gzb[o] = fv3::a2b_point(g, m, s, qgz, i, j);
+    if (k >= 1) {
+      auto qpp = [&](int ii, int jj) { return pp[O3(s, ii, jj, k)]; };
+      auto qpk = [&](int ii, int jj) { return pk3[O3(s, ii, jj, k)]; };
+      ppb[o] = fv3::a2b_point(g, m, s, qpp, i, j);
+      pk3b[o] = fv3::a2b_point(g, m, s, qpk, i, j);
+    } else {
+      ppb[o] = 0.0;
+      pk3b[o] = top_value;
+    }
+    if (k < nz) {
+      auto qdp = [&](int ii, int jj) { return delp[O3(s, ii, jj, k)]; };
+      wk1[o] = fv3::a2b_point(g, m, s, qdp, i, j);
+    }
+  });
+  // replace pp, pk3, gz by their B-grid values; calc_u / calc_v (:23-112)
+  fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, 0, nz + 1, FV_LAMBDA(int s, int i, int j, int k) {
+    const int64_t o = O3(s, i, j, k), o2 = O2(s, i, j);
+    pp[o] = ppb[o];
+    pk3[o] = pk3b[o];
+    gz[o] = gzb[o];
+    if (k == nz) return;
+    if (i <= iec) {
+      const double wk0 = pk3b[o + sk] - pk3b[o], wkx = pk3b[o + 1 + sk] - pk3b[o + 1];
+      const double a = gzb[o + sk] - gzb[o + 1], b = gzb[o] - gzb[o + 1 + sk];
+      const double du = dt / (wk0 + wkx) * (a * (pk3b[o + 1 + sk] - pk3b[o]) + b * (pk3b[o + sk] - pk3b[o + 1]));
+      u[o] = (u[o] + du + dt / (wk1[o] + wk1[o + 1]) * (a * (ppb[o + 1 + sk] - ppb[o]) + b * (ppb[o + sk] - ppb[o + 1]))) * m.rdx[o2];
+    }
+    if (j <= jec) {
+      const double wk0 = pk3b[o + sk] - pk3b[o], wky = pk3b[o + sj + sk] - pk3b[o + sj];
+      const double a = gzb[o + sk] - gzb[o + sj], b = gzb[o] - gzb[o + sj + sk];
+      const double dv = dt / (wk0 + wky) * (a * (pk3b[o + sj + sk] - pk3b[o]) + b * (pk3b[o + sk] - pk3b[o + sj]));
+      v[o] = (v[o] + dv + dt / (wk1[o] + wk1[o + sj]) * (a * (ppb[o + sj + sk] - ppb[o]) + b * (ppb[o + sk] - ppb[o + sj]))) * m.rdy[o2];
+    }
+  });
+  return fv3::check_launch("fv3_nh_p_grad");
+}
+
+// rf: per-level damping factor 1/(1+rfvals) (host-computed, ray_fast.py:22-38); n_rf = number of top levels with
+// pfull < rf_cutoff, n_nudge = number with pfull < rf_cutoff_nudge, p_ref = sum of dp_ref over the latter.
+int fv3_ray_fast(fv3_ctx *ctx, double *u, double *v, double *w, const double *rf, int n_rf, int n_nudge, double p_ref,
+                 void *stream) {
+  const fv3_geom g = ctx->g;
+  const fv3_grid m = ctx->m;
+  const int h = g.halo;
+  const int isc = h, iec = h + g.nx - 1, jsc = h, jec = h + g.ny - 1;
+  const double *dp = m.dp_ref;
+  const int hydrostatic = ctx->c.hydrostatic;
+  fv3::launch2d(ctx, (cudaStream_t)stream, isc, iec + 2, jsc, jec + 2, FV_LAMBDA(int s, int i, int j) {
+    const int64_t c0 = O3(s, i, j, 0), sk = g.sk;
+    auto damp = [&](double *q) {
+      double dm = 0.0;
+      for (int k = 0; k < n_rf; ++k) {
+        const double qv = q[c0 + k * sk];
+        const double d = (1.0 - rf[k]) * dp[k] * qv;
+        dm = k == 0 ? d : dm + d;
+        q[c0 + k * sk] = qv * rf[k];
+      }
+      for (int k = 0; k < n_nudge; ++k) q[c0 + k * sk] = q[c0 + k * sk] + dm / p_ref;
+    };
+    if (i <= iec) damp(u);
+    if (j <= jec) damp(v);
+    if (!hydrostatic && i <= iec && j <= jec)
+      for (int k = 0; k < n_rf; ++k) w[c0 + k * sk] = w[c0 + k * sk] * rf[k];
+  });
+  return fv3::check_launch("fv3_ray_fast");
+}
+
+int fv3_del2cubed(fv3_ctx *ctx, double *qdel, double cd, int nmax, int nk, void *stream) {
+  const fv3_geom g = ctx->g;
+  const fv3_grid m = ctx->m;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int h = g.halo;
+  const int isc = h, iec = h + g.nx - 1, jsc = h, jec = h + g.ny - 1;
+  const int ntimes = nmax < 3 ? nmax : 3;
+  double *tmp = fv3::scratch_field(ctx, 16);
+  double *bufs[2] = {qdel, tmp};
+  int cur = 0;
+  for (int n = 0; n < ntimes; ++n) {
+    const int nt = ntimes - (n + 1);
+    const double *qo = bufs[cur];
+    double *qn = bufs[1 - cur];
+    fv3::launch3d(ctx, st, isc - nt, iec + 1 + nt, jsc - nt, jec + 1 + nt, 0, nk, FV_LAMBDA(int s, int i, int j, int k) {
+      const bool W = fv3::on_west(g, s), E = fv3::on_east(g, s), S = fv3::on_south(g, s), N = fv3::on_north(g, s);
+      const double third = 1.0 / 3.0;
+      auto q0 = [&](int ii, int jj) { return qo[O3(s, ii, jj, k)]; };
+      // corner_fill (del2cubed.py:25-56)
+      auto qf = [&](int ii, int jj) {
+        if (W && S) {
+          if (ii == isc && jj == jsc) return (q0(ii, jj) + q0(ii - 1, jj) + q0(ii, jj - 1)) * third;
+          if (ii == isc - 1 && jj == jsc) return (q0(ii + 1, jj) + q0(ii, jj) + q0(ii + 1, jj - 1)) * third;
+          if (ii == isc && jj == jsc - 1) return (q0(ii, jj + 1) + q0(ii - 1, jj + 1) + q0(ii, jj)) * third;
+        }
+        if (E && S) {
+          if (ii == iec && jj == jsc) return (q0(ii, jj) + q0(ii + 1, jj) + q0(ii, jj - 1)) * third;
+          if (ii == iec + 1 && jj == jsc) return (q0(ii - 1, jj) + q0(ii, jj) + q0(ii - 1, jj - 1)) * third;
+          if (ii == iec && jj == jsc - 1) return (q0(ii, jj + 1) + q0(ii + 1, jj + 1) + q0(ii, jj)) * third;
+        }
+        if (E && N) {
+          if (ii == iec && jj == jec) return (q0(ii, jj) + q0(ii + 1, jj) + q0(ii, jj + 1)) * third;
+          if (ii == iec + 1 && jj == jec) return (q0(ii - 1, jj) + q0(ii, jj) + q0(ii - 1, jj + 1)) * third;
+          if (ii == iec && jj == jec + 1) return (q0(ii, jj - 1) + q0(ii + 1, jj - 1) + q0(ii, jj)) * third;
+        }
+        if (W && N) {
+          if (ii == isc && jj == jec) return (q0(ii, jj) + q0(ii - 1, jj) + q0(ii, jj + 1)) * third;
+          if (ii == isc - 1 && jj == jec) return (q0(ii + 1, jj) + q0(ii, jj) + q0(ii + 1, jj + 1)) * third;
+          if (ii == isc && jj == jec + 1) return (q0(ii, jj - 1) + q0(ii - 1, jj - 1) + q0(ii, jj)) * third;
+        }
+        return q0(ii, jj);
+      };
+      auto qx = [&](int ii, int jj) {
+        if (nt > 0) fv3::corner_x(g, s, ii, jj);
+        return qf(ii, jj);
+      };
+      auto qy = [&](int ii, int jj) {
+        if (nt > 0) fv3::corner_y(g, s, ii, jj);
+        return qf(ii, jj);
+      };
+      auto fx = [&](int ii, int jj) { return m.del6_v[O2(s, ii, jj)] * (qx(ii - 1, jj) - qx(ii, jj)); };
+      auto fy = [&](int ii, int jj) { return m.del6_u[O2(s, ii, jj)] * (qy(ii, jj - 1) - qy(ii, jj)); };
+      // the copy `qdel = q` keeps the y-corner-copied field (the last in-place copy) outside the compute domain
+      const double base = qy(i, j);
+      qn[O3(s, i, j, k)] = base + cd * m.rarea[O2(s, i, j)] * (fx(i, j) - fx(i + 1, j) + fy(i, j) - fy(i, j + 1));
+    });
+    cur = 1 - cur;
+  }
+  if (cur == 1) {
+    fv3::launch3d(ctx, st, isc, iec + 1, jsc, jec + 1, 0, nk, FV_LAMBDA(int s, int i, int j, int k) {
+      const int64_t o = O3(s, i, j, k);
+      qdel[o] = tmp[o];
+    });
+  }
+  return fv3::check_launch("fv3_del2cubed");
+}
+
+int fv3_apply_diffusive_heating(fv3_ctx *ctx, const double *delp, const double *delz, const double *cappa,
+                                const double *heat_source, double *pt, double delt_time_factor, int nk, void *stream) {
+  const fv3_geom g = ctx->g;
+  const int h = g.halo;
+  const double RDG = -287.05 / 9.80665, CV_AIR = 1004.6 - 287.05;
+  fv3::launch3d(ctx, (cudaStream_t)stream, h, h + g.nx, h, h + g.ny, 0, nk, FV_LAMBDA(int s, int i, int j, int k) {
+    const int64_t o = O3(s, i, j, k);
+    const double cp = cappa[o];
+    const double pkz = pow(RDG * delp[o] / delz[o] * pt[o], cp / (1.0 - cp));
+    const double dtmp = heat_source[o] / (CV_AIR * delp[o]);
+    const double lim = k == 0 ? delt_time_factor * 0.1 : (k == 1 ? delt_time_factor * 0.5 : delt_time_factor);
+    const double deltmin = fv3::rsign(fv3::dmin(lim, fabs(dtmp)), dtmp);
+    pt[o] = pt[o] + deltmin / pkz;
+  });
+  return fv3::check_launch("fv3_apply_diffusive_heating");
+}
+
+}  // extern "C"

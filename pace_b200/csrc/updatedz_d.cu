@@ -1,0 +1,86 @@
+// Height of the Lagrangian surfaces on the D grid.
+//   fv3_update_dz_d <- UpdateHeightOnDGrid.__call__ (fv3core/pace/fv3core/stencils/updatedzd.py:283-356)
+#include "common.h"
+
+extern "C" int fv3_fvtp2d(fv3_ctx *, const double *, const double *, const double *, const double *, const double *,
+                          double *, double *, const double *, const double *, const double *, int, const double *,
+                          const double *, int, int, void *);
+extern "C" int fv3_delnflux_nosg(fv3_ctx *, const double *, double *, double *, const double *, const double *, int,
+                                 int, void *);
+
+namespace {
+constexpr double DZ_MIN = 2.0;
+constexpr int NKMAX = 96;
+}  // namespace
+
+extern "C" {
+
+int fv3_update_dz_d(fv3_ctx *ctx, const double *surface_height, double *height, const double *crx, const double *cry,
+                    const double *xfx, const double *yfx, double *ws, double dt, const double *gk, const double *beta,
+                    const double *gamma, const double *damp_col, const double *nord_col, int nmax, void *stream) {
+  const fv3_geom g = ctx->g;
+  const fv3_grid m = ctx->m;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int h = g.halo, nz = g.nz, sj = g.sj;
+  const int isc = h, iec = h + g.nx - 1, jsc = h, jec = h + g.ny - 1, ied = iec + h, jed = jec + h;
+  if (nz + 1 > NKMAX) {
+    fv3::set_error("fv3_update_dz_d: nz too large");
+    return -1;
+  }
+  double *crx_i = fv3::scratch_field(ctx, 16), *cry_i = fv3::scratch_field(ctx, 17);
+  double *xfx_i = fv3::scratch_field(ctx, 18), *yfx_i = fv3::scratch_field(ctx, 19);
+  double *fx = fv3::scratch_field(ctx, 20), *fy = fv3::scratch_field(ctx, 21);
+  double *gx = fv3::scratch_field(ctx, 22), *gy = fv3::scratch_field(ctx, 23);
+  // cubic_spline_interpolation_from_layer_center_to_interfaces (updatedzd.py:157-196), 4 fields, full domain
+  fv3::launch3d(ctx, st, 0, ied + 1, 0, jed + 1, 0, 4, FV_LAMBDA(int s, int i, int j, int f) {
+    const double *qc = f == 0 ? crx : (f == 1 ? xfx : (f == 2 ? cry : yfx));
+    double *qi = f == 0 ? crx_i : (f == 1 ? xfx_i : (f == 2 ? cry_i : yfx_i));
+    const int64_t c0 = O3(s, i, j, 0), sk = g.sk;
+    double col[NKMAX];
+    {
+      const double xt1 = 2.0 * gk[0] * (gk[0] + 1.0);
+      col[0] = (xt1 * qc[c0] + qc[c0 + sk]) / beta[0];
+    }
+    for (int k = 1; k < nz; ++k) col[k] = (3.0 * (qc[c0 + (k - 1) * sk] + gk[k] * qc[c0 + k * sk]) - col[k - 1]) / beta[k];
+    {
+      const double gl = gk[nz - 1];
+      const double a_bot = 1.0 + gl * (gl + 1.5);
+      const double xt1 = 2.0 * gl * (gl + 1.0);
+      const double xt2 = gl * (gl + 0.5) - a_bot * gamma[nz - 1];
+      col[nz] = (xt1 * qc[c0 + (nz - 1) * sk] + qc[c0 + (nz - 2) * sk] - a_bot * col[nz - 1]) / xt2;
+    }
+    qi[c0 + nz * sk] = col[nz];
+    for (int k = nz - 1; k >= 0; --k) {
+      col[k] = col[k] - gamma[k] * col[k + 1];
+      qi[c0 + k * sk] = col[k];
+    }
+  });
+  int rc;
+  if ((rc = fv3_fvtp2d(ctx, height, crx_i, cry_i, xfx_i, yfx_i, fx, fy, nullptr, nullptr, nullptr, ctx->c.hord_tm, nullptr,
+                       nullptr, 0, nz + 1, stream)))
+    return rc;
+  if ((rc = fv3_delnflux_nosg(ctx, height, gx, gy, damp_col, nord_col, nmax, nz + 1, stream))) return rc;
+  // apply_height_fluxes (updatedzd.py:70-126): compute domain, BACKWARD monotonicity fix
+  fv3::launch2d(ctx, st, isc, iec + 1, jsc, jec + 1, FV_LAMBDA(int s, int i, int j) {
+    const int64_t c0 = O3(s, i, j, 0), sk = g.sk;
+    const double ar = m.area[O2(s, i, j)];
+    double below = 0.0;
+    for (int k = nz; k >= 0; --k) {
+      const int64_t o = c0 + k * sk;
+      const double area_after = ((ar + xfx_i[o] - xfx_i[o + 1]) + (ar + yfx_i[o] - yfx_i[o + sj])) - ar;
+      double hv = (height[o] * ar + fx[o] - fx[o + 1] + fy[o] - fy[o + sj]) / area_after +
+                  (gx[o] - gx[o + 1] + gy[o] - gy[o + sj]) / ar;
+      if (k == nz) {
+        ws[O2(s, i, j)] = (surface_height[O2(s, i, j)] - hv) / dt;
+      } else {
+        const double other = below + DZ_MIN;
+        hv = hv > other ? hv : other;
+      }
+      height[o] = hv;
+      below = hv;
+    }
+  });
+  return fv3::check_launch("fv3_update_dz_d");
+}
+
+}  // extern "C"
