@@ -191,6 +191,38 @@ int fv3_del2cubed(fv3_ctx *ctx, double *qdel, double cd, int nmax, int nk, void 
 int fv3_apply_diffusive_heating(fv3_ctx *ctx, const double *delp, const double *delz, const double *cappa,
                                 const double *heat_source, double *pt, double delt_time_factor, int nk, void *stream);
 
+/* ---- LagrangianToEulerian.__call__ (remapping.py:485-695) is issued by the Python class as the calls below.
+ *      tracers6: device array of 6 pointers qvapor, qliquid, qrain, qsnow, qice, qgraupel. */
+int fv3_remap_prep(fv3_ctx *ctx, double *const *tracers6, double *q_con, double *pt, double *cappa, double *delp,
+                   double *delz, const double *pe, double *pe1, double *pe2, double *dp2, double *ps, double *pn2,
+                   const double *peln, double *pk, double ptop, double akap, double r_vir, void *stream);
+/* MapSingle.__call__ (map_single.py:147-200), kord 9; iv = remap mode (1, 0, -1, -2); qs: NULL, a 2-D field
+ * (qs_is_2d = 1) or a 3-D field read at level 0; i_extra / j_extra = 1 for x- / y-interface fields (v / u). */
+int fv3_map_single(fv3_ctx *ctx, double *q1, const double *pe1, const double *pe2, const double *qs, int qs_is_2d,
+                   double qmin, int kord, int iv, int i_extra, int j_extra, void *stream);
+/* FillNegativeTracerValues.__call__ (fillz.py:15-163) for nq tracers (device array of nq pointers) */
+int fv3_fillz(fv3_ctx *ctx, double *const *tracers, int nq, const double *dp2, void *stream);
+int fv3_remap_post(fv3_ctx *ctx, double *const *tracers6, double *q_con, double *pkz, const double *pt, double *cappa,
+                   const double *delp, double *delz, double *peln, double *pe0, const double *pn2, double r_vir,
+                   void *stream);
+int fv3_remap_pressures(fv3_ctx *ctx, const double *pe, double *pe0, double *pe3, int dir, void *stream);
+int fv3_remap_finish(fv3_ctx *ctx, double *const *tracers6, const double *pe2, double *pe, double *pt, const double *pkz,
+                     int last_step, double dtmp, double r_vir, void *stream);
+/* ---- DynamicalCore.compute_preamble (fv_dynamics.py:440-483): fv_setup + pt_to_potential_density_pt */
+int fv3_fv_setup(fv3_ctx *ctx, double *const *tracers6, double *q_con, double *cvm, double *pkz, double *pt,
+                 double *cappa, const double *delp, const double *delz, double *dp1, void *stream);
+/* ---- omega_from_w (fv_dynamics.py:55-64) */
+int fv3_omega_from_w(fv3_ctx *ctx, const double *delp, const double *delz, const double *w, double *omga, void *stream);
+
+/* ---- TracerAdvection.__call__ (tracer_2d_1l.py:264-392) pieces; the transport itself is fv3_fvtp2d(hord_tr) */
+int fv3_tracer_flux_prep(fv3_ctx *ctx, double *cxd, double *cyd, double *mfxd, double *mfyd, double *xfx, double *yfx,
+                         int n_split, void *stream);
+int fv3_tracer_apply_mass_flux(fv3_ctx *ctx, const double *dp1, const double *mfx, const double *mfy, double *dp2,
+                               void *stream);
+int fv3_tracer_apply_flux(fv3_ctx *ctx, double *q, const double *dp1, const double *fx, const double *fy,
+                          const double *dp2, void *stream);
+int fv3_tracer_swap_dp(fv3_ctx *ctx, double *dp1, double *dp2, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

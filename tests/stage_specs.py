@@ -28,6 +28,7 @@ class StageSpec:
     interface_fields: Sequence[str] = ()
     regions: Dict[str, tuple] = dataclasses.field(default_factory=dict)  # output -> (i slice, j slice) compared
     check_untouched: bool = True
+    expected: Callable = None         # optional hook: golden dict -> golden dict with adjusted "out." entries
     tols: Dict[str, float] = dataclasses.field(default_factory=dict)  # per-output override of tol
     case: str = "c12"                 # golden case directory (c12 = first step, c12s2 = second step of the same run)
 
@@ -381,3 +382,78 @@ def golden_stage_files():
     for sp in SPECS.values():
         out.setdefault(sp.case, set()).add(sp.golden)
     return {k: sorted(v) for k, v in out.items()}
+
+
+# ---------------------------------------------------------------------------------------------
+# vertical remapping (second-step goldens)
+def _ptr_array(rt, qs):
+    import torch
+
+    return torch.tensor([q.ptr for q in qs], dtype=torch.int64).to(rt.device)
+
+
+def _make_map_single(n, iv, i_extra=0, j_extra=0):
+    def native(sf, qf, rt, q, d):
+        qs = q.get("qs")
+        rt.call("fv3_map_single", q["q1"].ptr, q["pe1"].ptr, q["pe2"].ptr, qs.ptr if (qs is not None and iv == -2) else None,
+                1, float(d.get("in.qmin", 0.0)), 9, iv, i_extra, j_extra)
+
+    reg = (slice(3, 3 + NX + i_extra), slice(3, 3 + NX + j_extra))
+    SPECS[f"map_single_{n}"] = StageSpec(f"map_single_{n}", f"MapSingle#{n}", ("q1",), _o_todo, native, tol=1e-12, near_zero=1e-13,
+                                         case=S2, regions={"q1": reg}, check_untouched=False)
+
+
+_make_map_single(0, 1)        # pt
+_make_map_single(1, 0)        # qvapor
+_make_map_single(9, -2)       # w
+_make_map_single(10, 1)       # delz
+_make_map_single(11, -1, j_extra=1)   # u
+_make_map_single(12, -1, i_extra=1)   # v
+
+
+def _n_fillz(sf, qf, rt, q, d):
+    names = ["qvapor", "qliquid", "qrain", "qice", "qsnow", "qgraupel", "qo3mr", "qsgs_tke"]
+    arr = _ptr_array(rt, [q["tracers." + n] for n in names])
+    rt.call("fv3_fillz", arr.data_ptr(), 8, q["dp2"].ptr)
+
+
+SPECS["fillz"] = StageSpec("fillz", "Fillz#0", tuple("tracers." + n for n in ("qvapor", "qliquid", "qrain", "qice")), _o_todo,
+                           _n_fillz, tol=5e-6, case=S2, regions={"tracers." + n: COMPUTE for n in ("qvapor", "qliquid", "qrain", "qice")},
+                           check_untouched=False)
+
+
+def _n_fvsetup(sf, qf, rt, q, d):
+    arr = _ptr_array(rt, [q[n] for n in ("qvapor", "qliquid", "qrain", "qsnow", "qice", "qgraupel")])
+    rt.call("fv3_fv_setup", arr.data_ptr(), q["q_con"].ptr, q["cvm"].ptr, q["pkz"].ptr, q["pt"].ptr, q["cappa"].ptr,
+            q["delp"].ptr, q["delz"].ptr, q["dp1"].ptr)
+
+
+def _fvsetup_expected(d):
+    """fv3_fv_setup also applies pt_to_potential_density_pt: expected pt comes from the PtAdjust golden."""
+    d2 = H.load_stage(S2, 0, "PtAdjust#0")
+    d = dict(d)
+    d["out.pt"] = d2["out.pt"]
+    return d
+
+
+SPECS["fv_setup"] = StageSpec("fv_setup", "FVSetup#0", ("q_con", "cvm", "pkz", "cappa", "dp1", "pt"), _o_todo, _n_fvsetup, tol=1e-13,
+                              case=S2, regions={n: COMPUTE for n in ("q_con", "cvm", "pkz", "cappa", "dp1", "pt")},
+                              check_untouched=False, expected=_fvsetup_expected)
+
+
+def _n_remap(sf, qf, rt, q, d):
+    from pace_b200.fv3core._config import baroclinic_config
+    from pace_b200.fv3core.stencils.remapping import LagrangianToEulerian
+
+    tr = {n: q["tracers." + n] for n in ("qvapor", "qliquid", "qrain", "qice", "qsnow", "qgraupel", "qo3mr", "qsgs_tke")}
+    l2e = LagrangianToEulerian(sf, qf, baroclinic_config(NX).remapping, rt.grid_data.area_64, 8, None, tr)
+    l2e(tr, q["pt"], q["delp"], q["delz"], q["peln"], q["u"], q["v"], q["w"], q["cappa"], q["q_con"], q["q_cld"], q["pkz"],
+        q["pk"], q["pe"], q["hs"], q["ps"], q["wsd"], None, None, q["dp1"], f(d, "ptop"), f(d, "akap"), f(d, "zvir"),
+        bool(d["in.last_step"]), f(d, "consv_te"), f(d, "mdt"))
+
+
+_RM_OUT = ("pt", "delp", "delz", "peln", "u", "v", "w", "cappa", "q_con", "pkz", "pk", "pe", "ps", "tracers.qvapor")
+SPECS["remapping"] = StageSpec(
+    "remapping", "Remapping#0", _RM_OUT, _o_todo, _n_remap, tol=1e-11, near_zero=1e-13, case=S2, check_untouched=False,
+    tols={"w": 5e-6},
+    regions={**{n: COMPUTE for n in _RM_OUT}, "u": _YI, "v": _XI})
