@@ -223,6 +223,9 @@ int fv3_tracer_apply_flux(fv3_ctx *ctx, double *q, const double *dp1, const doub
                           const double *dp2, void *stream);
 int fv3_tracer_swap_dp(fv3_ctx *ctx, double *dp1, double *dp2, void *stream);
 
+/* ---- CubedToLatLon, c2l_ord = 4 (stencils/pace/stencils/c2l_ord.py:41-66); the u/v halo update is done by the caller */
+int fv3_c2l_ord4(fv3_ctx *ctx, const double *u, const double *v, double *ua, double *va, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

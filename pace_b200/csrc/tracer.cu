@@ -74,3 +74,31 @@ int fv3_tracer_swap_dp(fv3_ctx *ctx, double *dp1, double *dp2, void *stream) {
 }
 
 }  // extern "C"
+
+extern "C" {
+
+// CubedToLatLon ord4_transform (stencils/pace/stencils/c2l_ord.py:41-66) on the compute domain
+int fv3_c2l_ord4(fv3_ctx *ctx, const double *u, const double *v, double *ua, double *va, void *stream) {
+  const fv3_geom g = ctx->g;
+  const fv3_grid m = ctx->m;
+  const int h = g.halo, sj = g.sj;
+  const int isc = h, iec = h + g.nx - 1, jsc = h, jec = h + g.ny - 1;
+  const double C1 = 1.125, C2 = -0.125;
+  fv3::launch3d(ctx, (cudaStream_t)stream, isc, iec + 1, jsc, jec + 1, 0, g.nz, FV_LAMBDA(int s, int i, int j, int k) {
+    const bool W = fv3::on_west(g, s), E = fv3::on_east(g, s), S = fv3::on_south(g, s), N = fv3::on_north(g, s);
+    const int64_t o = O3(s, i, j, k), o2 = O2(s, i, j);
+    double utmp, vtmp;
+    if ((S && j == jsc) || (N && j == jec) || (W && i == isc) || (E && i == iec)) {
+      utmp = 2.0 * (u[o] * m.dx[o2] + u[o + sj] * m.dx[o2 + sj]) / (m.dx[o2] + m.dx[o2 + sj]);
+      vtmp = 2.0 * ((v[o] * m.dy[o2]) + (v[o + 1] * m.dy[o2 + 1])) / (m.dy[o2] + m.dy[o2 + 1]);
+    } else {
+      utmp = C2 * (u[o - sj] + u[o + 2 * sj]) + C1 * (u[o] + u[o + sj]);
+      vtmp = C2 * (v[o - 1] + v[o + 2]) + C1 * (v[o] + v[o + 1]);
+    }
+    ua[o] = m.a11[o2] * utmp + m.a12[o2] * vtmp;
+    va[o] = m.a21[o2] * utmp + m.a22[o2] * vtmp;
+  });
+  return fv3::check_launch("fv3_c2l_ord4");
+}
+
+}  // extern "C"
