@@ -24,6 +24,7 @@ HORIZONTAL_2D = [
 ]
 DAMPING_2D = ["divg_u", "divg_v", "del6_u", "del6_v"]
 COLUMNS = ["ak", "bk", "dp_ref", "p"]
+INIT_HOST = ["lon", "lat", "lon_agrid", "lat_agrid", "ee1", "ee2", "es1", "ew2", "ak", "bk", "area"]
 
 
 def _as_2d(name, arr, shape):
@@ -60,7 +61,25 @@ class GridData:
                 columns[name] = torch.as_tensor(col).to(qf.device)
         scalars = {k: float(per_rank[0][k]) for k in ("ptop", "p_ref") if k in per_rank[0]}
         scalars["ks"] = int(per_rank[0].get("ks", _ks_from_bk(per_rank[0].get("bk"))))
-        return cls(fields, columns, scalars)
+        out = cls(fields, columns, scalars)
+        # host copies of what the analytic initial conditions read (positions and grid unit vectors)
+        out._host = [{k: np.asarray(r[k]) for k in INIT_HOST if k in r} for r in per_rank]
+        return out
+
+    @classmethod
+    def new_from_generation(cls, qf: QuantityFactory, comm, nz: int = None) -> "GridData":
+        """Metric terms of this process's subdomains from pace_b200.util.grid.generation (the role of
+        GridData.new_from_metric_terms(MetricTerms(...)) in the reference, helper.py:60-120)."""
+        from . import generation
+
+        nx_tile = comm.decomposition.n_tile
+        per_rank = generation.generate(nx_tile, comm.decomposition.layout, comm.local_ranks, nz or qf.geometry.nz)
+        out = cls.from_arrays(qf, per_rank)
+        out._per_rank = per_rank
+        return out
+
+    def host_dicts(self):
+        return self._host
 
     def __getattr__(self, name):
         for store in ("_fields", "_columns", "_scalars"):
@@ -100,6 +119,12 @@ class DampingCoefficients:
         for name in DAMPING_2D:
             fields[name] = qf.from_array(np.stack([np.asarray(r[prefix + name]) for r in per_rank]), dims, "")
         return cls(fields, per_rank[0][prefix + "da_min"], per_rank[0][prefix + "da_min_c"])
+
+    @classmethod
+    def new_from_generation(cls, qf: QuantityFactory, grid_data: "GridData"):
+        """From the same generated terms as GridData.new_from_generation (DampingCoefficients.new_from_metric_terms
+        in the reference, helper.py:20-60)."""
+        return cls.from_arrays(qf, grid_data._per_rank)
 
     def __getattr__(self, name):
         d = self.__dict__.get("_fields", {})
