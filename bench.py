@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""Benchmark of the FV3 dycore hot path: seconds per C128 L79 baroclinic timestep (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one `DynamicalCore.step_dynamics` (k_split=2 remap cycles x n_split=6 acoustic substeps, tracer advection
+of 8 tracers, vertical remap) on the analytic Jablonowski-Williamson state, C128 L79, layout (2,2) = 24 subdomains spread
+over the N GPUs.  Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+from datetime import timedelta
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# compulsory field passes (reads + writes of distinct 3-D fields) of each fused stage
+STAGE_PASSES = {
+    "fv3_c_sw": 15, "fv3_update_dz_c": 4, "fv3_riem_solver_c": 8, "fv3_p_grad_c": 7, "fv3_d_sw": 34,
+    "fv3_update_dz_d": 6, "fv3_riem_solver3": 13, "fv3_nh_p_grad": 8, "fv3_ray_fast": 6,
+}
+SUBSTEP_PASSES, TRACER_PASSES, REMAP_PASSES, EXTRA_BYTES_PER_CELL = 101, 85, 36, 100
+
+
+def algorithmic_bytes_per_cell(k_split, n_split):
+    return k_split * (n_split * SUBSTEP_PASSES * 8 + TRACER_PASSES * 8 + REMAP_PASSES * 8) + EXTRA_BYTES_PER_CELL
+
+
+def build_dycore(nx, layout, nz, k_split, n_split, device, process_comm=None, all_tracers=True):
+    from pace_b200.fv3core._config import baroclinic_config
+    from pace_b200.fv3core.initialization import baroclinic
+    from pace_b200.fv3core.runtime import Runtime
+    from pace_b200.fv3core.stencil_factory import GridIndexing, StencilFactory
+    from pace_b200.fv3core.stencils.fv_dynamics import DynamicalCore
+    from pace_b200.util.communicator import CubedSphereCommunicator, ProcessComm
+    from pace_b200.util.grid.helper import DampingCoefficients, GridData
+    from pace_b200.util.sizer import QuantityFactory, SubtileGridSizer
+
+    comm = CubedSphereCommunicator.from_layout(process_comm or ProcessComm(), (layout, layout), nx, nz, device=device)
+    sizer = SubtileGridSizer.from_tile_params(nx, nx, nz, 3, {}, (layout, layout))
+    qf = QuantityFactory(sizer, comm.geometry, device)
+    gd = GridData.new_from_generation(qf, comm)
+    damp = DampingCoefficients.new_from_generation(qf, gd)
+    cfg = baroclinic_config(nx, (layout, layout), n_split=n_split, k_split=k_split)
+    rt = Runtime(comm, qf, gd, damp, cfg)
+    sf = StencilFactory(None, GridIndexing.from_sizer_and_communicator(qf.sizer, comm), rt)
+    state = baroclinic.init_baroclinic_state(gd, qf, adiabatic=False, hydrostatic=False, moist_phys=True, comm=comm,
+                                             fill_all_tracers=all_tracers)
+    dycore = DynamicalCore(comm, gd, sf, qf, damp, cfg, state.phis, state, timedelta(seconds=cfg.dt_atmos))
+    return dycore, state, comm, rt, gd
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                smax.append(float(c[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.f.name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_port_seconds_per_step(nx_sample, layout, k_split, n_split, steps, warmup, nx_target, verbose=False):
+    """The CPU port (host simulation of the same stage functors, OpenMP over all host cores; oracle/hostsim.py) timed on
+    a bounded sample of the workload and scaled by the cell-count ratio to the target resolution."""
+    import torch
+
+    from oracle import hostsim
+
+    hostsim.install(openmp=True)
+    dycore, state, comm, rt, gd = build_dycore(nx_sample, layout, 79, k_split, n_split, "cpu")
+    for _ in range(warmup):
+        dycore.step_dynamics(state)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        dycore.step_dynamics(state)
+    dt = (time.perf_counter() - t0) / steps
+    assert bool(torch.isfinite(state.pt.data[:, 3:-4, 3:-4, :79]).all()), "CPU port produced non-finite values"
+    return dt * (nx_target / nx_sample) ** 2, dt
+
+
+def run_reference_arm(args):
+    """`--impl reference`: the CPU implementation of the path on the host cores.  The reference itself is Python + a
+    GT4Py tool-chain that is neither installable nor present on the GPU box, so this arm times the CPU port
+    (oracle/hostsim.py), as the tier contract prescribes when the reference cannot be compiled."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    total = args.steps + args.warmup
+    # calibrate on c24 and pick the largest sample that keeps the whole run within ~4 minutes
+    scaled, t24 = cpu_port_seconds_per_step(24, args.layout, args.k_split, args.n_split, 1, 0, args.nx)
+    nx_sample = 24
+    for cand in (48, 32):
+        if t24 * (cand / 24) ** 2 * total < 200.0:
+            nx_sample = cand
+            break
+    value, raw = cpu_port_seconds_per_step(nx_sample, args.layout, args.k_split, args.n_split, args.steps, args.warmup, args.nx)
+    sample = (f"C{nx_sample} L79 layout ({args.layout},{args.layout}) full timestep (k_split={args.k_split}, n_split={args.n_split}), "
+              f"{raw:.3f} s/step measured, scaled by cell count x{(args.nx / nx_sample) ** 2:.2f} to C{args.nx}")
+    line = {
+        "impl": "reference", "metric": "C128L79 baroclinic dycore s/timestep", "value": value, "unit": "s/timestep",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": value * 1e3,
+        "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": "s/timestep", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "s/timestep", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {
+        "workload": f"C{args.nx} L79 baroclinic (Jablonowski-Williamson), layout ({args.layout},{args.layout}) = "
+                    f"{6 * args.layout ** 2} subdomains, DynamicalCore.step_dynamics, k_split={args.k_split}, n_split={args.n_split}, "
+                    f"dt_atmos=225, 8 non-zero tracers, do_sat_adj off",
+        "nx_tile": args.nx, "nz": 79, "layout": [args.layout, args.layout], "k_split": args.k_split, "n_split": args.n_split,
+        "subdomains_per_gpu": 6 * args.layout ** 2 // max(args.gpus, 1),
+        "l2_policy": "working set (>1 GB of fp64 fields per GPU) exceeds the 126 MB L2; no explicit flush",
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nx", type=int, default=128)
+    ap.add_argument("--layout", type=int, default=2)
+    ap.add_argument("--k-split", type=int, default=2)
+    ap.add_argument("--n-split", type=int, default=6)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--stage-table", action="store_true", help="print the per-stage timing table to stderr")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        print("bench.py: raising --warmup to the required minimum of 3", file=sys.stderr)
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+
+    from pace_b200 import _lib
+    from pace_b200.util.communicator import ProcessComm
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the hot path has no CPU fallback)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local_rank)
+    device = f"cuda:{local_rank}"
+    pc = None
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device(device))
+        pc = ProcessComm.from_torch_distributed()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    lib = _lib.load()
+    dycore, state, comm, rt, gd = build_dycore(args.nx, args.layout, 79, args.k_split, args.n_split, device, pc)
+    n_local = comm.geometry.n_sub
+    cells_local = n_local * comm.geometry.nx * comm.geometry.ny * 79
+    cells_total = 6 * args.nx * args.nx * 79
+    from pace_b200.fv3core.dycore_state import FIELDS
+
+    def storage(q):
+        """The contiguous allocation behind a Quantity (I-fastest, padded rows) — what is copied to / from the host."""
+        d = q.data
+        return d._base if d._base is not None else d
+
+    state0 = {n: storage(getattr(state, n)).clone() for n in FIELDS}
+
+    # ---- device-resident timing (value) ------------------------------------------------------------------
+    for _ in range(args.warmup):
+        dycore.step_dynamics(state)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    prof = _lib.PROFILE = _lib.StageProfile()
+    l0 = lib.fv3_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        dycore.step_dynamics(state)
+    e1.record()
+    barrier()
+    launches = lib.fv3_launch_count() - l0
+    _lib.PROFILE = None
+    ms = e0.elapsed_time(e1) / args.steps
+    clocks = sampler.stop() if sampler is not None else None
+    finite = bool(torch.isfinite(state.pt.data[:, 3:-4, 3:-4, :79]).all())
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    stages = prof.summary()
+
+    # ---- end to end through the public API with HOST buffers (e2e) --------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        names = list(state0)
+        host_in = {n: state0[n].cpu().pin_memory() for n in names}
+        host_out = {n: torch.empty_like(host_in[n]).pin_memory() for n in names}
+        h2d = sum(v.numel() * 8 for v in host_in.values())
+        d2h = h2d
+
+        def e2e_step():
+            for n in names:
+                storage(getattr(state, n)).copy_(host_in[n], non_blocking=True)
+            dycore.step_dynamics(state)
+            for n in names:
+                host_out[n].copy_(storage(getattr(state, n)), non_blocking=True)
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        n_e2e = max(2, min(args.steps, 5))
+        for _ in range(n_e2e):
+            e2e_step()
+        a1.record()
+        barrier()
+        t = torch.tensor([a0.elapsed_time(a1) / n_e2e], dtype=torch.float64, device=device)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": float(t.item()) / 1e3, "unit": "s/timestep", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+               "steps": n_e2e, "note": "full DycoreState copied from pinned host memory before and back to it after every step_dynamics"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant stage -------------------------------------------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    table = sorted(((t_ms, n, name) for name, (n, t_ms) in stages.items()), reverse=True)
+    if args.stage_table:
+        for t_ms, n, name in table:
+            per = t_ms / n
+            extra = ""
+            if name in STAGE_PASSES:
+                gb = STAGE_PASSES[name] * 8 * cells_local / 1e9
+                extra = f"  {gb / (per / 1e3):8.1f} GB/s algorithmic"
+            print(f"{name:32s} calls {n:5d}  total {t_ms:9.3f} ms  avg {per * 1e3:9.1f} us{extra}", file=sys.stderr)
+    dom = next(((t_ms, n, name) for t_ms, n, name in table if name in STAGE_PASSES), None)
+    roofline = None
+    if dom is not None:
+        t_ms, n, name = dom
+        bytes_per_launch = STAGE_PASSES[name] * 8 * cells_local
+        achieved = bytes_per_launch / (t_ms / n / 1e3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(name)
+        roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
+                    "avg_launch_ms": t_ms / n, "share_of_step": t_ms / (ms * args.steps),
+                    "step_achieved_GBps": algorithmic_bytes_per_cell(args.k_split, args.n_split) * cells_total / (ms / 1e3) / 1e9,
+                    "step_frac": algorithmic_bytes_per_cell(args.k_split, args.n_split) * cells_total / (ms / 1e3) / 1e9 / (peak * world)}
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        cores = os.cpu_count() or 1
+        os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+        _prod = _lib._lib
+        try:
+            scaled, raw = cpu_port_seconds_per_step(24, args.layout, args.k_split, args.n_split, 1, 1, args.nx)
+        finally:
+            _lib.install(_prod)   # back to the CUDA library
+        cpu = {"value": scaled, "unit": "s/timestep", "cores": cores, "kind": "port",
+               "sample": f"c24 L79 layout ({args.layout},{args.layout}) full timestep (same k_split/n_split), {raw:.3f} s/step measured after 1 warm-up, "
+                         f"scaled by cell count x{(args.nx / 24) ** 2:.2f} to C{args.nx}"}
+
+    line = {
+        "metric": "C128L79 baroclinic dycore s/timestep", "value": ms / 1e3, "unit": "s/timestep", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args), "clocks": clocks,
+        "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "finite": finite,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -92,6 +92,8 @@ const char *fv3_last_error(void);
 int fv3_abi_version(void);
 /* 1 when this library was built as the CPU host-simulation of the kernels (tests only), 0 for CUDA. */
 int fv3_is_hostsim(void);
+/* CUDA kernels launched by this library since it was loaded (bench.py reports the difference over the timed region) */
+int64_t fv3_launch_count(void);
 /* number of 3-D scratch fields fv3_create needs (scratch_bytes >= n * ss * n_sub * 8) */
 int fv3_scratch_fields(void);
 

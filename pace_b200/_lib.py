@@ -1,8 +1,9 @@
 """ctypes binding of libfv3b200.so (include/fv3_b200.h).
 
-The product path has NO CPU fallback: `load()` raises if the CUDA library has not been built.  The only other
-library that can be loaded is the host-simulation build of the same kernel sources, and only when a test sets
-PACE_B200_HOSTSIM=1 explicitly (CPU-only CI of host-side orchestration; never used by bench.py or smoke()).
+The product path has NO CPU fallback: `load()` only ever loads the CUDA library pace_b200/libfv3b200.so and raises
+if it has not been built.  (CPU-only CI of the host-side orchestration injects a host-simulation build of the same
+kernel sources through `install()`; that build and its loader live under oracle/hostsim.py — test infrastructure —
+and nothing in this package can reach them.)
 """
 import ctypes as C
 import os
@@ -91,26 +92,9 @@ def parse_header(path=HEADER):
 
 
 
-def hostsim_requested() -> bool:
-    return os.environ.get("PACE_B200_HOSTSIM", "0") == "1"
-
-
-def load():
-    """Load (once) and return the native library.  Fails loudly when it is missing."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if hostsim_requested():
-        path = os.path.join(os.path.dirname(HERE), "tests", "_hostsim", "libfv3b200_hostsim.so")
-    else:
-        path = os.path.join(HERE, "libfv3b200.so")
-    if not os.path.exists(path):
-        raise RuntimeError(
-            f"pace_b200: native library {path} not found; build it with `python -m pace_b200.build` "
-            "(there is no CPU fallback for the hot path)"
-        )
-    lib = C.CDLL(path)
-    vp, i32, i64, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_double
+def bind(lib):
+    """Declare restype/argtypes of every entry point of include/fv3_b200.h on a loaded ctypes library."""
+    vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
     lib.fv3_create.restype = vp
     lib.fv3_create.argtypes = [C.POINTER(Geom), C.POINTER(Config), C.POINTER(Grid), vp, i64]
     lib.fv3_destroy.argtypes = [vp]
@@ -118,16 +102,69 @@ def load():
     lib.fv3_is_hostsim.restype = i32
     lib.fv3_abi_version.restype = i32
     lib.fv3_scratch_fields.restype = i32
+    lib.fv3_launch_count.restype = i64
     for name, argtypes in parse_header().items():
         if name in ("fv3_create", "fv3_destroy"):
             continue
         fn = getattr(lib, name)  # AttributeError here = header declares a symbol the library lacks
         fn.restype = i32
         fn.argtypes = argtypes
-    if bool(lib.fv3_is_hostsim()) != hostsim_requested():
-        raise RuntimeError("pace_b200: loaded library kind does not match PACE_B200_HOSTSIM")
+    return lib
+
+
+def load():
+    """Load (once) and return the CUDA library.  Fails loudly when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = os.path.join(HERE, "libfv3b200.so")
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"pace_b200: native library {path} not found; build it with `python -m pace_b200.build` "
+            "(there is no CPU fallback for the hot path)"
+        )
+    lib = bind(C.CDLL(path))
+    if lib.fv3_is_hostsim():
+        raise RuntimeError("pace_b200: libfv3b200.so is not a CUDA build")
     _lib = lib
     return lib
+
+
+def install(lib):
+    """Use an already bound library object instead of loading libfv3b200.so (tests only: oracle/hostsim.py)."""
+    global _lib
+    _lib = lib
+
+
+class StageProfile:
+    """CUDA-event timing of every C-ABI stage call on the launching stream (bench.py's roofline pass).
+
+    Switched on with `_lib.PROFILE = StageProfile()`; off (None) by default so the hot path records nothing.
+    """
+
+    def __init__(self):
+        self.records = []   # (stage name, start event, end event)
+
+    def begin(self):
+        import torch
+
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def end(self, name, e0):
+        self.records.append((name, e0, self.begin()))
+
+    def summary(self):
+        """{stage: (calls, total ms)} — call after torch.cuda.synchronize()."""
+        out = {}
+        for name, e0, e1 in self.records:
+            n, t = out.get(name, (0, 0.0))
+            out[name] = (n + 1, t + e0.elapsed_time(e1))
+        return out
+
+
+PROFILE = None
 
 
 def check(lib, rc, what=""):

@@ -1,7 +1,6 @@
-"""Build recipe for libfv3b200.so (CUDA, sm_100a) — and, for tests only, its CPU host-simulation twin.
+"""Build recipe for libfv3b200.so (CUDA, sm_100a).
 
     python -m pace_b200.build            # nvcc cross-compiles without a GPU
-    python -m pace_b200.build --hostsim  # g++ build of the same kernel sources for CPU-only CI
 
 The CUDA library is built IN-TREE (pace_b200/libfv3b200.so) so it travels with the repo snapshot.
 """
@@ -15,14 +14,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 CUDA_LIB = os.path.join(HERE, "libfv3b200.so")
-HOSTSIM_LIB = os.path.join(ROOT, "tests", "_hostsim", "libfv3b200_hostsim.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--extended-lambda",
     "-fmad=false",  # fp64 parity with the numpy backend: no FMA contraction (DESIGN.md "parity budget")
     "-Xcompiler", "-fPIC",
 ]
-GXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-DFV3_HOSTSIM", "-x", "c++", "-w"]
 
 
 def _sources():
@@ -40,7 +37,7 @@ def _headers():
     return glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(ROOT, "include", "*.h"))
 
 
-def _compile_all(cmd_for, objdir, verbose):
+def compile_all(cmd_for, objdir, verbose=False):
     os.makedirs(objdir, exist_ok=True)
     jobs = []
     objs = []
@@ -66,7 +63,7 @@ def _compile_all(cmd_for, objdir, verbose):
 def build_cuda(verbose=False, extra_flags=()):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objdir = os.path.join(HERE, "build", "cuda")
-    objs, changed, outs = _compile_all(
+    objs, changed, outs = compile_all(
         lambda s, o: [nvcc] + NVCC_FLAGS + list(extra_flags) + ["-c", s, "-o", o], objdir, verbose)
     if changed or not os.path.exists(CUDA_LIB):
         cmd = [nvcc, "-shared", "-o", CUDA_LIB] + objs + ["-lcudart"]
@@ -76,24 +73,10 @@ def build_cuda(verbose=False, extra_flags=()):
     return CUDA_LIB, outs
 
 
-def build_hostsim(verbose=False):
-    gxx = os.environ.get("CXX", "g++")
-    objdir = os.path.join(ROOT, "tests", "_hostsim", "obj")
-    objs, changed, _ = _compile_all(lambda s, o: [gxx] + GXX_FLAGS + ["-c", s, "-o", o], objdir, verbose)
-    if changed or not os.path.exists(HOSTSIM_LIB):
-        r = subprocess.run([gxx, "-shared", "-o", HOSTSIM_LIB] + objs, capture_output=True, text=True)
-        if r.returncode != 0:
-            raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
-    return HOSTSIM_LIB
-
-
 if __name__ == "__main__":
     v = "-v" in sys.argv
-    if "--hostsim" in sys.argv:
-        print(build_hostsim(v))
-    else:
-        lib, outs = build_cuda(v, ["-Xptxas", "-v"] if "--ptxas" in sys.argv else [])
-        for o in outs:
-            if o.strip():
-                print(o)
-        print(lib)
+    lib, outs = build_cuda(v, ["-Xptxas", "-v"] if "--ptxas" in sys.argv else [])
+    for o in outs:
+        if o.strip():
+            print(o)
+    print(lib)

@@ -36,6 +36,7 @@ namespace fv3 {
 
 void set_error(const char *msg);
 int check_launch(const char *what);
+extern long long g_launches;  // kernels launched by this library since load (fv3_launch_count)
 
 // scratch field n (3-D, all subdomains)
 static inline double *scratch_field(const fv3_ctx *ctx, int n) {
@@ -82,13 +83,18 @@ inline void launch3d(const fv3_ctx *ctx, cudaStream_t st, int i0, int i1, int j0
   if (ni <= 0 || nj <= 0 || nk <= 0) return;
 #ifdef FV3_HOSTSIM
   (void)st;
-  for (int s = 0; s < ctx->g.n_sub; ++s)
+  const int n_sub = ctx->g.n_sub;
+#ifdef FV3_HOSTSIM_OMP
+#pragma omp parallel for collapse(2) schedule(static)
+#endif
+  for (int s = 0; s < n_sub; ++s)
     for (int k = k0; k < k1; ++k)
       for (int j = j0; j < j1; ++j)
         for (int i = i0; i < i1; ++i) f(s, i, j, k);
 #else
   dim3 grid((ni * nj + 127) / 128, nk, ctx->g.n_sub);
   k3d<<<grid, 128, 0, st>>>(f, i0, ni, j0, nj, k0);
+  ++g_launches;
 #endif
 }
 
@@ -99,12 +105,17 @@ inline void launch2d(const fv3_ctx *ctx, cudaStream_t st, int i0, int i1, int j0
   if (ni <= 0 || nj <= 0) return;
 #ifdef FV3_HOSTSIM
   (void)st;
-  for (int s = 0; s < ctx->g.n_sub; ++s)
+  const int n_sub = ctx->g.n_sub;
+#ifdef FV3_HOSTSIM_OMP
+#pragma omp parallel for collapse(2) schedule(static)
+#endif
+  for (int s = 0; s < n_sub; ++s)
     for (int j = j0; j < j1; ++j)
       for (int i = i0; i < i1; ++i) f(s, i, j);
 #else
   dim3 grid((ni * nj + 63) / 64, ctx->g.n_sub);
   k2d<<<grid, 64, 0, st>>>(f, i0, ni, j0, nj);
+  ++g_launches;
 #endif
 }
 
@@ -114,12 +125,16 @@ inline void launch1d(cudaStream_t st, int64_t n, int ny, int nz, F f) {
   if (n <= 0 || ny <= 0 || nz <= 0) return;
 #ifdef FV3_HOSTSIM
   (void)st;
+#ifdef FV3_HOSTSIM_OMP
+#pragma omp parallel for collapse(2) schedule(static)
+#endif
   for (int z = 0; z < nz; ++z)
     for (int y = 0; y < ny; ++y)
       for (int64_t e = 0; e < n; ++e) f(e, y, z);
 #else
   dim3 grid((unsigned)((n + 127) / 128), ny, nz);
   k1d<<<grid, 128, 0, st>>>(f, n);
+  ++g_launches;
 #endif
 }
 

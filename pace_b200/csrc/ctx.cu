@@ -3,6 +3,7 @@
 
 namespace fv3 {
 static char g_err[512] = "";
+long long g_launches = 0;
 void set_error(const char *msg) { snprintf(g_err, sizeof g_err, "%s", msg); }
 int check_launch(const char *what) {
 #ifdef FV3_HOSTSIM
@@ -31,6 +32,7 @@ int fv3_is_hostsim(void) {
 #endif
 }
 int fv3_scratch_fields(void) { return 40; }
+int64_t fv3_launch_count(void) { return (int64_t)fv3::g_launches; }
 
 fv3_ctx *fv3_create(const fv3_geom *geom, const fv3_config *config, const fv3_grid *grid, void *scratch,
                     int64_t scratch_bytes) {

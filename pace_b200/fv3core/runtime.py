@@ -48,7 +48,7 @@ class Runtime:
         self.damping = damping
         self.config = config
         self.device = quantity_factory.device
-        if self.device.type != "cuda" and not _lib.hostsim_requested():
+        if self.device.type != "cuda" and not self.lib.fv3_is_hostsim():
             raise RuntimeError("pace_b200 runs on CUDA devices only (no CPU fallback)")
         g = comm.geometry
         cfg = _lib.Config()
@@ -94,8 +94,12 @@ class Runtime:
         return self.comm.stream_ptr()
 
     def call(self, name, *args):
+        prof = _lib.PROFILE
+        e0 = prof.begin() if prof is not None else None
         rc = getattr(self.lib, name)(self.ctx, *args, self.stream())
         _lib.check(self.lib, rc, name)
+        if prof is not None:
+            prof.end(name, e0)
 
     def __del__(self):
         try:

@@ -171,6 +171,8 @@ class HaloUpdater:
         gp = ctypes.byref(comm.c_geom)
         self._inflight = True
         reqs = []
+        prof = _lib.PROFILE
+        e0 = prof.begin() if prof is not None else None
         if self._send or self._recv:
             import torch.distributed as dist
 
@@ -189,6 +191,8 @@ class HaloUpdater:
                                                 L["src_comp"].data_ptr(), L["sign"].data_ptr(), self._n_local, stream),
                        "fv3_halo_gather")
         self._pending = (reqs, ptrs, n_fields)
+        if prof is not None:
+            prof.end("halo_start", e0)
 
     def wait(self):
         if not self._inflight:

@@ -1,7 +1,7 @@
 """pytest configuration.
 
 `-m "not gpu"` (CPU box): oracle vs golden vectors, host logic, C-ABI symbol checks, and the kernel sources
-exercised through the HOST-SIMULATION build (tests/_hostsim, g++ -DFV3_HOSTSIM) — a test-only device that is
+exercised through the HOST-SIMULATION build (oracle/hostsim.py, g++ -DFV3_HOSTSIM) — a test-only device that is
 enabled here explicitly and can never be reached from the product API by accident.
 `-m gpu` (B200): parity tests proper, through the CUDA C-ABI library.
 """
@@ -18,10 +18,9 @@ import torch  # noqa: E402
 
 HAVE_GPU = torch.cuda.is_available()
 if not HAVE_GPU:
-    os.environ["PACE_B200_HOSTSIM"] = "1"
-    from pace_b200 import build as _build
+    from oracle import hostsim as _hostsim
 
-    _build.build_hostsim()
+    _hostsim.install()
 
 
 def pytest_configure(config):
