@@ -224,6 +224,12 @@ int fv3_tracer_apply_mass_flux(fv3_ctx *ctx, const double *dp1, const double *mf
 int fv3_tracer_apply_flux(fv3_ctx *ctx, double *q, const double *dp1, const double *fx, const double *fy,
                           const double *dp2, void *stream);
 int fv3_tracer_swap_dp(fv3_ctx *ctx, double *dp1, double *dp2, void *stream);
+/* One whole sub-cycle of the loop at tracer_2d_1l.py:341-392 for nq tracers (device array of pointers): dp2 from the
+ * mass fluxes, transport of every tracer with hord (8) and its flux application, then dp2 stored and - when swap != 0,
+ * i.e. another sub-cycle follows - exchanged with dp1.  Same results as the four calls above issued per tracer. */
+int fv3_tracer_subcycle(fv3_ctx *ctx, double *const *tracers, int nq, double *dp1, double *dp2, const double *mfx,
+                        const double *mfy, const double *cx, const double *cy, const double *xfx, const double *yfx,
+                        int hord, int swap, void *stream);
 
 /* ---- CubedToLatLon, c2l_ord = 4 (stencils/pace/stencils/c2l_ord.py:41-66); the u/v halo update is done by the caller */
 int fv3_c2l_ord4(fv3_ctx *ctx, const double *u, const double *v, double *ua, double *va, void *stream);

@@ -142,4 +142,65 @@ FV_HD double a2b_point(const fv3_geom &g, const fv3_grid &m, int s, Q q, int i, 
   return 0.5 * (qxx + qyy);
 }
 
+// ---- plane-resident form (plane.h): the reference's three temporaries qx, qy, qout_edges are built ONCE per plane
+// in shared memory instead of being re-derived inside every thread.
+//   SQ: qin plane   QX / QY: ppm_volume_mean_x / _y   OUT: B-grid result (tile-edge values first, then the rest)
+// qin / qout are global pointers to the start of the (s, k) plane; each array holds nj * sj doubles.
+template <class B>
+FV_HD void a2b_plane(const fv3_geom &g, const fv3_grid &m, int s, const B &b, const double *qin, double *SQ, double *QX,
+                     double *QY, double *OUT) {
+  const int sj = g.sj, h = g.halo;
+  const int isc = h, iec = h + g.nx - 1, jsc = h, jec = h + g.ny - 1;
+  const bool W = on_west(g, s), E = on_east(g, s), S = on_south(g, s), N = on_north(g, s);
+  const int nwi = g.ni - 1, nwj = g.nj - 1;
+  b.par(nwi * nwj, [&](int t) {
+    const int j = t / nwi, i = t - j * nwi;
+    SQ[j * sj + i] = qin[j * sj + i];
+  });
+  auto q = [&](int ii, int jj) { return SQ[jj * sj + ii]; };
+  // qx on corner columns isc..iec+1, rows jsc-2..jec+2; qy on rows jsc..jec+1, columns isc-2..iec+2; edge values
+  const int nxc = g.nx + 1, nyc = g.ny + 1, nxw = g.nx + 4, nyw = g.ny + 4;
+  b.par(nxc * nyw + nxw * nyc, [&](int t) {
+    if (t < nxc * nyw) {
+      const int jr = t / nxc, i = isc + (t - jr * nxc), j = jsc - 2 + jr;
+      QX[j * sj + i] = a2b_qx(g, m, s, q, i, j);
+    } else {
+      const int t2 = t - nxc * nyw;
+      const int jr = t2 / nxw, i = isc - 2 + (t2 - jr * nxw), j = jsc + jr;
+      QY[j * sj + i] = a2b_qy(g, m, s, q, i, j);
+    }
+  });
+  b.par(nxc * nyc, [&](int t) {
+    const int jr = t / nxc, i = isc + (t - jr * nxc), j = jsc + jr;
+    if ((W && i == isc) || (E && i == iec + 1) || (S && j == jsc) || (N && j == jec + 1))
+      OUT[j * sj + i] = a2b_edge_value(g, m, s, q, i, j);
+  });
+  b.par(nxc * nyc, [&](int t) {
+    const int jr = t / nxc, i = isc + (t - jr * nxc), j = jsc + jr;
+    if ((W && i == isc) || (E && i == iec + 1) || (S && j == jsc) || (N && j == jec + 1)) return;
+    auto qx = [&](int jj) { return QX[jj * sj + i]; };
+    auto qy = [&](int ii) { return QY[j * sj + ii]; };
+    double qxx, qyy;
+    if (S && j == jsc + 1) {
+      const double upper = A2B::a2 * (qx(j - 1) + qx(j + 2)) + A2B::a1 * (qx(j) + qx(j + 1));
+      qxx = A2B::c1 * (qx(j - 1) + qx(j)) + A2B::c2 * (OUT[(j - 1) * sj + i] + upper);
+    } else if (N && j == jec) {
+      const double lower = A2B::a2 * (qx(j - 3) + qx(j)) + A2B::a1 * (qx(j - 2) + qx(j - 1));
+      qxx = A2B::c1 * (qx(j - 1) + qx(j)) + A2B::c2 * (OUT[(j + 1) * sj + i] + lower);
+    } else {
+      qxx = A2B::a2 * (qx(j - 2) + qx(j + 1)) + A2B::a1 * (qx(j - 1) + qx(j));
+    }
+    if (W && i == isc + 1) {
+      const double right = A2B::a2 * (qy(i - 1) + qy(i + 2)) + A2B::a1 * (qy(i) + qy(i + 1));
+      qyy = A2B::c1 * (qy(i - 1) + qy(i)) + A2B::c2 * (OUT[j * sj + i - 1] + right);
+    } else if (E && i == iec) {
+      const double left = A2B::a2 * (qy(i - 3) + qy(i)) + A2B::a1 * (qy(i - 2) + qy(i - 1));
+      qyy = A2B::c1 * (qy(i - 1) + qy(i)) + A2B::c2 * (OUT[j * sj + i + 1] + left);
+    } else {
+      qyy = A2B::a2 * (qy(i - 2) + qy(i + 1)) + A2B::a1 * (qy(i - 1) + qy(i));
+    }
+    OUT[j * sj + i] = 0.5 * (qxx + qyy);
+  });
+}
+
 }  // namespace fv3

@@ -22,7 +22,7 @@ FV_HD double contravariant(double v1, double v2, double cosa, double rsin2) { re
 void corner_fill_2cells(const fv3_ctx *ctx, cudaStream_t st, double *delp, double *pt, double *w, int dir) {
   const fv3_geom g = ctx->g;
   const int h = g.halo, isc = h, iec = h + g.nx - 1, jsc = h, jec = h + g.ny - 1;
-  fv3::launch3d(ctx, st, 0, 8, 0, 3, 0, g.nz, FV_LAMBDA(int s, int id, int f, int k) {
+  fv3::launch3d(ctx, st, 0, 8, 0, 3, 0, g.nz, FV_LAMBDA(int s, int id, int f, int k) { FV_DEV_GM
     const int corner = id / 2, d = id % 2 + 1;
     const bool west = (corner == 0 || corner == 2), south = (corner < 2);
     if (!((west ? fv3::on_west(g, s) : fv3::on_east(g, s)) && (south ? fv3::on_south(g, s) : fv3::on_north(g, s))))
@@ -60,7 +60,7 @@ int fv3_c_sw(fv3_ctx *ctx, double *delp, double *pt, const double *u, const doub
   const int nord = ctx->c.nord;
 
   // K1: utmp/vtmp (d2a2c_vect.py:19-65) on the full domain; zero delpc/ptc (c_sw.py:19-27)
-  fv3::launch3d(ctx, st, 0, ied + 1, 0, jed + 1, 0, nz, FV_LAMBDA(int s, int i, int j, int k) {
+  fv3::launch3d(ctx, st, 0, ied + 1, 0, jed + 1, 0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     const bool W = fv3::on_west(g, s), E = fv3::on_east(g, s), S = fv3::on_south(g, s), N = fv3::on_north(g, s);
     const int64_t o = O3(s, i, j, k);
     delpc[o] = 0.0;
@@ -84,7 +84,7 @@ int fv3_c_sw(fv3_ctx *ctx, double *delp, double *pt, const double *u, const doub
   });
 
   // K2: contravariant A-grid winds on compute + 2 (d2a2c_vect.py:68-78)
-  fv3::launch3d(ctx, st, isc - 2, iec + 3, jsc - 2, jec + 3, 0, nz, FV_LAMBDA(int s, int i, int j, int k) {
+  fv3::launch3d(ctx, st, isc - 2, iec + 3, jsc - 2, jec + 3, 0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     const int64_t o = O3(s, i, j, k), o2 = O2(s, i, j);
     const double a = utmp[o], b = vtmp[o], cs = m.cosa_s[o2], r2 = m.rsin2[o2];
     ua[o] = contravariant(a, b, cs, r2);
@@ -93,7 +93,7 @@ int fv3_c_sw(fv3_ctx *ctx, double *delp, double *pt, const double *u, const doub
 
   // K2b: corner fills of utmp (3 cells), ua (2 cells) in x and vtmp, va in y (d2a2c_vect.py:81-88,157-164);
   // read and written point sets are disjoint, so x and y fills share one launch.
-  fv3::launch3d(ctx, st, 0, 12, 0, 2, 0, nz, FV_LAMBDA(int s, int id, int dir, int k) {
+  fv3::launch3d(ctx, st, 0, 12, 0, 2, 0, nz, FV_LAMBDA(int s, int id, int dir, int k) { FV_DEV_GM
     const int corner = id / 3, d = id % 3 + 1;  // corner: 0 sw, 1 se, 2 nw, 3 ne
     const bool west = (corner == 0 || corner == 2), south = (corner < 2);
     if (!((west ? fv3::on_west(g, s) : fv3::on_east(g, s)) && (south ? fv3::on_south(g, s) : fv3::on_north(g, s))))
@@ -117,7 +117,7 @@ int fv3_c_sw(fv3_ctx *ctx, double *delp, double *pt, const double *u, const doub
 
   // K3: C-grid winds uc, vc and geo-adjusted contravariant fluxes ut, vt
   // (d2a2c_vect.py:91-228, c_sw.py:156-199)
-  fv3::launch3d(ctx, st, isc - 1, iec + 3, jsc - 1, jec + 3, 0, nz, FV_LAMBDA(int s, int i, int j, int k) {
+  fv3::launch3d(ctx, st, isc - 1, iec + 3, jsc - 1, jec + 3, 0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     const bool W = fv3::on_west(g, s), E = fv3::on_east(g, s), S = fv3::on_south(g, s), N = fv3::on_north(g, s);
     const int64_t o = O3(s, i, j, k), o2 = O2(s, i, j);
     if (j <= jec + 1) {
@@ -170,7 +170,7 @@ int fv3_c_sw(fv3_ctx *ctx, double *delp, double *pt, const double *u, const doub
 
   // K4: divergence at cell corners (c_sw.py:31-154)
   if (nord > 0) {
-    fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, 0, nz, FV_LAMBDA(int s, int i, int j, int k) {
+    fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, 0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
       const bool W = fv3::on_west(g, s), E = fv3::on_east(g, s), S = fv3::on_south(g, s), N = fv3::on_north(g, s);
       auto uf = [&](int ii, int jj) {
         const int64_t o = O3(s, ii, jj, k), o2 = O2(s, ii, jj);
@@ -201,7 +201,7 @@ int fv3_c_sw(fv3_ctx *ctx, double *delp, double *pt, const double *u, const doub
   corner_fill_2cells(ctx, st, delp, pt, w, 0);
 
   // K5: first-order upwind x-fluxes (c_sw.py:229-258)
-  fv3::launch3d(ctx, st, isc - 1, iec + 3, jsc - 1, jec + 2, 0, nz, FV_LAMBDA(int s, int i, int j, int k) {
+  fv3::launch3d(ctx, st, isc - 1, iec + 3, jsc - 1, jec + 2, 0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     const int64_t o = O3(s, i, j, k);
     const double utc = ut[o];
     const int64_t ou = utc > 0.0 ? o - 1 : o;
@@ -214,7 +214,7 @@ int fv3_c_sw(fv3_ctx *ctx, double *delp, double *pt, const double *u, const doub
   corner_fill_2cells(ctx, st, delp, pt, w, 1);
 
   // K6: transport of delp, pt, w; upstream kinetic energy and vorticity (c_sw.py:261-364)
-  fv3::launch3d(ctx, st, isc - 1, iec + 2, jsc - 1, jec + 2, 0, nz, FV_LAMBDA(int s, int i, int j, int k) {
+  fv3::launch3d(ctx, st, isc - 1, iec + 2, jsc - 1, jec + 2, 0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     const bool W = fv3::on_west(g, s), E = fv3::on_east(g, s), S = fv3::on_south(g, s), N = fv3::on_north(g, s);
     const int64_t o = O3(s, i, j, k), o2 = O2(s, i, j);
     double fy1a, fya, fy2a, fy1b, fyb, fy2b;
@@ -248,7 +248,7 @@ int fv3_c_sw(fv3_ctx *ctx, double *delp, double *pt, const double *u, const doub
   });
 
   // K7: absolute vorticity at cell corners (c_sw.py:367-408)
-  fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, 0, nz, FV_LAMBDA(int s, int i, int j, int k) {
+  fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, 0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     const bool W = fv3::on_west(g, s), E = fv3::on_east(g, s), S = fv3::on_south(g, s), N = fv3::on_north(g, s);
     const int64_t o = O3(s, i, j, k), o2 = O2(s, i, j);
     const double fxv = m.dxc[o2] * uc[o], fyv = m.dyc[o2] * vc[o];
@@ -261,7 +261,7 @@ int fv3_c_sw(fv3_ctx *ctx, double *delp, double *pt, const double *u, const doub
   });
 
   // K8: C-grid wind update (c_sw.py:411-480)
-  fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, 0, nz, FV_LAMBDA(int s, int i, int j, int k) {
+  fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, 0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     const bool W = fv3::on_west(g, s), E = fv3::on_east(g, s), S = fv3::on_south(g, s), N = fv3::on_north(g, s);
     const int64_t o = O3(s, i, j, k), o2 = O2(s, i, j);
     if (i <= iec) {

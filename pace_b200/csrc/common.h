@@ -30,7 +30,23 @@ struct fv3_ctx {
   fv3_grid m;
   double *scratch;
   int64_t scratch_bytes;
+  uint64_t uid;  // unique per fv3_create (a recycled address must not look like the previous context)
 };
+
+// Geometry and metric-term pointer tables live in __constant__ memory (one copy per translation unit, refreshed by
+// the launchers whenever the active context changes): kernels read them as c[bank][offset] operands instead of
+// carrying ~550 bytes of by-value closure that a dynamic index (edge[s]) would force into local memory.
+#ifdef FV3_HOSTSIM
+#define FV_DEV_GM
+#else
+static __constant__ fv3_geom c_g;
+static __constant__ fv3_grid c_m;
+#define FV_DEV_GM                 \
+  const fv3_geom &g = c_g;        \
+  const fv3_grid &m = c_m;        \
+  (void)g;                        \
+  (void)m;
+#endif
 
 namespace fv3 {
 
@@ -76,6 +92,16 @@ __global__ void __launch_bounds__(128) k1d(F f, int64_t n) {
 }
 #endif
 
+#ifndef FV3_HOSTSIM
+static uint64_t tu_active_uid = 0;
+static inline void activate(const fv3_ctx *ctx, cudaStream_t st) {
+  if (tu_active_uid == ctx->uid) return;
+  cudaMemcpyToSymbolAsync(c_g, &ctx->g, sizeof(fv3_geom), 0, cudaMemcpyHostToDevice, st);
+  cudaMemcpyToSymbolAsync(c_m, &ctx->m, sizeof(fv3_grid), 0, cudaMemcpyHostToDevice, st);
+  tu_active_uid = ctx->uid;
+}
+#endif
+
 // f(s, i, j, k) for i in [i0, i1), j in [j0, j1), k in [k0, k1), all local subdomains
 template <class F>
 inline void launch3d(const fv3_ctx *ctx, cudaStream_t st, int i0, int i1, int j0, int j1, int k0, int k1, F f) {
@@ -92,6 +118,7 @@ inline void launch3d(const fv3_ctx *ctx, cudaStream_t st, int i0, int i1, int j0
       for (int j = j0; j < j1; ++j)
         for (int i = i0; i < i1; ++i) f(s, i, j, k);
 #else
+  activate(ctx, st);
   dim3 grid((ni * nj + 127) / 128, nk, ctx->g.n_sub);
   k3d<<<grid, 128, 0, st>>>(f, i0, ni, j0, nj, k0);
   ++g_launches;
@@ -113,6 +140,7 @@ inline void launch2d(const fv3_ctx *ctx, cudaStream_t st, int i0, int i1, int j0
     for (int j = j0; j < j1; ++j)
       for (int i = i0; i < i1; ++i) f(s, i, j);
 #else
+  activate(ctx, st);
   dim3 grid((ni * nj + 63) / 64, ctx->g.n_sub);
   k2d<<<grid, 64, 0, st>>>(f, i0, ni, j0, nj);
   ++g_launches;

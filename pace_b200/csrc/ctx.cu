@@ -55,6 +55,8 @@ fv3_ctx *fv3_create(const fv3_geom *geom, const fv3_config *config, const fv3_gr
   ctx->m = *grid;
   ctx->scratch = (double *)scratch;
   ctx->scratch_bytes = scratch_bytes;
+  static uint64_t next_uid = 0;
+  ctx->uid = ++next_uid;
   return ctx;
 }
 

@@ -5,6 +5,7 @@
 // Sub-stages call the same internal routines as the stand-alone entry points (fxadv.cu, fvtp2d.cu).
 #include "a2b.h"
 #include "common.h"
+#include "plane.h"
 #include "ppm.h"
 
 extern "C" int fv3_fv_prep(fv3_ctx *, const double *, const double *, double *, double *, double *, double *, double *,
@@ -56,10 +57,16 @@ FV_HD void bgrid_corner_y(const fv3_geom &g, int s, int &i, int &j) {
 void a2b_ord4_launch(const fv3_ctx *ctx, cudaStream_t st, const double *qin, double *qout, int k0, int k1) {
   const fv3_geom g = ctx->g;
   const fv3_grid m = ctx->m;
-  const Ix x = make_ix(g);
-  fv3::launch3d(ctx, st, x.isc, x.iec + 2, x.jsc, x.jec + 2, k0, k1, FV_LAMBDA(int s, int i, int j, int k) {
-    auto q = [&](int ii, int jj) { return qin[O3(s, ii, jj, k)]; };
-    qout[O3(s, i, j, k)] = fv3::a2b_point(g, m, s, q, i, j);
+  const int PL = g.nj * g.sj;
+  fv3::launch_planes(ctx, st, k0, k1, 4 * PL, FV_LAMBDA(int s, int k, const fv3::Block &b) { FV_DEV_GM
+    double *SQ = b.sm, *QX = SQ + PL, *QY = QX + PL, *OUT = QY + PL;
+    const int64_t ob = O3(s, 0, 0, k);
+    fv3::a2b_plane(g, m, s, b, qin + ob, SQ, QX, QY, OUT);
+    const int sj2 = g.sj, nxc = g.nx + 1, h2 = g.halo;
+    b.par(nxc * (g.ny + 1), [&](int t) {
+      const int jr = t / nxc, p = (h2 + jr) * sj2 + h2 + (t - jr * nxc);
+      qout[ob + p] = OUT[p];
+    });
   });
 }
 
@@ -70,7 +77,7 @@ void divg_iteration(const fv3_ctx *ctx, cudaStream_t st, const double *dold, dou
   const fv3_grid m = ctx->m;
   const Ix x = make_ix(g);
   const int isc = x.isc, iec = x.iec, jsc = x.jsc, jec = x.jec;
-  fv3::launch3d(ctx, st, isc - nt, iec + nt + 2, jsc - nt, jec + nt + 2, k0, g.nz, FV_LAMBDA(int s, int i, int j, int k) {
+  fv3::launch3d(ctx, st, isc - nt, iec + nt + 2, jsc - nt, jec + nt + 2, k0, g.nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     const bool W = fv3::on_west(g, s), E = fv3::on_east(g, s), S = fv3::on_south(g, s), N = fv3::on_north(g, s);
     auto dgx = [&](int ii, int jj) {
       if (fillc) bgrid_corner_x(g, s, ii, jj);
@@ -132,7 +139,7 @@ void divergence_damping(fv3_ctx *ctx, cudaStream_t st, const double *u, const do
   const double *d2_bg = c->d2_divg;
   if (k0 > 0) {
     // levels [0, k0): second-order damping (divergence_damping.py:21-118,504-548)
-    fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, 0, k0, FV_LAMBDA(int s, int i, int j, int k) {
+    fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, 0, k0, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
       const bool W = fv3::on_west(g, s), E = fv3::on_east(g, s), S = fv3::on_south(g, s), N = fv3::on_north(g, s);
       auto ucd = [&](int ii, int jj) {  // u_contra * dyc at (x centre, y interface)
         const int64_t o = O3(s, ii, jj, k), o2 = O2(s, ii, jj);
@@ -168,7 +175,7 @@ void divergence_damping(fv3_ctx *ctx, cudaStream_t st, const double *u, const do
     });
   }
   // levels [k0, nz): delpc <- divg_d, then nord Laplacian iterations on divg_d
-  fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, k0, nz, FV_LAMBDA(int s, int i, int j, int k) {
+  fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, k0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     const int64_t o = O3(s, i, j, k);
     delpc[o] = divg_d[o];
   });
@@ -182,7 +189,7 @@ void divergence_damping(fv3_ctx *ctx, cudaStream_t st, const double *u, const do
     cur = 1 - cur;
   }
   if (cur == 1) {  // result sits in the scratch buffer: bring it back over the final (compute) domain
-    fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, k0, nz, FV_LAMBDA(int s, int i, int j, int k) {
+    fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, k0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
       const int64_t o = O3(s, i, j, k);
       divg_d[o] = tmp[o];
     });
@@ -196,7 +203,7 @@ void divergence_damping(fv3_ctx *ctx, cudaStream_t st, const double *u, const do
   }
   // a2b_ord4 of the relative vorticity + Smagorinsky-type diffusion + high-order damping
   // (divergence_damping.py:590-632)
-  fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, k0, nz, FV_LAMBDA(int s, int i, int j, int k) {
+  fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, k0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     const int64_t o = O3(s, i, j, k);
     double vo;
     if (dddmp < 1e-5) {
@@ -289,7 +296,7 @@ int fv3_d_sw(fv3_ctx *ctx, double *delpc, double *delp, double *pt, double *u, d
                        c->dn_damp_vt, c->nmax_v, nz, stream)))
     return rc;
   // flux_capacitor (d_sw.py:29-50) on the full domain
-  fv3::launch3d(ctx, st, 0, ied + 1, 0, jed + 1, 0, nz, FV_LAMBDA(int s, int i, int j, int k) {
+  fv3::launch3d(ctx, st, 0, ied + 1, 0, jed + 1, 0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     const int64_t o = O3(s, i, j, k);
     cx[o] = cx[o] + crx[o];
     cy[o] = cy[o] + cry[o];
@@ -298,7 +305,7 @@ int fv3_d_sw(fv3_ctx *ctx, double *delpc, double *delp, double *pt, double *u, d
   });
   // w: del-n fluxes of damp_w * w, heat dissipation (d_sw.py:53-103)
   if ((rc = fv3_delnflux_nosg(ctx, w, fx2, fy2, c->dn_damp_w_c, c->nord_w, c->nmax_w, nz, stream))) return rc;
-  fv3::launch3d(ctx, st, isc, iec + 1, jsc, jec + 1, 0, nz, FV_LAMBDA(int s, int i, int j, int k) {
+  fv3::launch3d(ctx, st, isc, iec + 1, jsc, jec + 1, 0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     const int64_t o = O3(s, i, j, k);
     double hs = 0.0;
     if (damp_w[k] > 1e-5) {
@@ -314,7 +321,7 @@ int fv3_d_sw(fv3_ctx *ctx, double *delpc, double *delp, double *pt, double *u, d
   if ((rc = fv3_fvtp2d(ctx, q_con, crx, cry, xfx, yfx, gxq, gyq, fx, fy, delp, cfg.hord_dp, c->nord_t, c->dn_damp_t, c->nmax_t, nz, stream))) return rc;
   if ((rc = fv3_fvtp2d(ctx, pt, crx, cry, xfx, yfx, gxp, gyp, fx, fy, delp, cfg.hord_tm, c->nord_v, c->dn_damp_vt, c->nmax_v, nz, stream))) return rc;
   // apply_fluxes (w, q_con), apply_pt_delp_fluxes, adjust_w_and_qcon (d_sw.py:106-160,331-346) on the compute domain
-  fv3::launch3d(ctx, st, isc, iec + 1, jsc, jec + 1, 0, nz, FV_LAMBDA(int s, int i, int j, int k) {
+  fv3::launch3d(ctx, st, isc, iec + 1, jsc, jec + 1, 0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     const int64_t o = O3(s, i, j, k);
     const double ra = m.rarea[O2(s, i, j)];
     const double dp0 = delp[o];
@@ -337,7 +344,7 @@ int fv3_d_sw(fv3_ctx *ctx, double *delpc, double *delp, double *pt, double *u, d
     fv3::set_error("fv3_d_sw: hord_mt >= 8 is not implemented");
     return -1;
   }
-  fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, 0, nz, FV_LAMBDA(int s, int i, int j, int k) {
+  fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, 0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     const bool W = fv3::on_west(g, s), E = fv3::on_east(g, s), S = fv3::on_south(g, s), N = fv3::on_north(g, s);
     const int64_t o = O3(s, i, j, k), o2 = O2(s, i, j);
     const bool ie_ = (W && i == isc) || (E && i == iec + 1), je_ = (S && j == jsc) || (N && j == jec + 1);
@@ -379,20 +386,20 @@ int fv3_d_sw(fv3_ctx *ctx, double *delpc, double *delp, double *pt, double *u, d
     ke[o] = kev;
   });
   // relative vorticity on the A grid, full domain (d_sw.py:301-328)
-  fv3::launch3d(ctx, st, 0, ied + 1, 0, jed + 1, 0, nz, FV_LAMBDA(int s, int i, int j, int k) {
+  fv3::launch3d(ctx, st, 0, ied + 1, 0, jed + 1, 0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     const int64_t o = O3(s, i, j, k), o2 = O2(s, i, j);
     const double rdy_tmp = m.rarea[o2] * m.dx[o2], rdx_tmp = m.rarea[o2] * m.dy[o2];
     vort_a[o] = (u[o] - u[o + sj] * m.dx[o2 + sj] / m.dx[o2]) * rdy_tmp + (v[o + 1] * m.dy[o2 + 1] / m.dy[o2] - v[o]) * rdx_tmp;
   });
   divergence_damping(ctx, st, u, v, va, vort_b, ua, divgd, vc, uc, delpc, ke, vort_a, dt, c);
   // absolute vorticity and its transport (d_sw.py:1131-1147)
-  fv3::launch3d(ctx, st, 0, ied + 1, 0, jed + 1, 0, nz, FV_LAMBDA(int s, int i, int j, int k) {
+  fv3::launch3d(ctx, st, 0, ied + 1, 0, jed + 1, 0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     const int64_t o = O3(s, i, j, k);
     abs_vort[o] = vort_a[o] + m.f0[O2(s, i, j)];
   });
   if ((rc = fv3_fvtp2d(ctx, abs_vort, crx, cry, xfx, yfx, fx, fy, nullptr, nullptr, nullptr, cfg.hord_vt, nullptr, nullptr, 0, nz, stream))) return rc;
   // u_and_v_from_ke (d_sw.py:439-477)
-  fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, 0, nz, FV_LAMBDA(int s, int i, int j, int k) {
+  fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, 0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     const int64_t o = O3(s, i, j, k), o2 = O2(s, i, j);
     if (i <= iec) u[o] = u[o] * m.dx[o2] + ke[o] - ke[o + 1] + fy[o];
     if (j <= jec) v[o] = v[o] * m.dy[o2] + ke[o] - ke[o + sj] - fx[o];
@@ -401,7 +408,7 @@ int fv3_d_sw(fv3_ctx *ctx, double *delpc, double *delp, double *pt, double *u, d
   if ((rc = fv3_delnflux_nosg(ctx, vort_a, ut, vt, c->dn_damp_vt_c, c->nord_v, c->nmax_v, nz, stream))) return rc;
   // vort_differencing + heat_source_from_vorticity_damping (d_sw.py:349-577) on the compute domain
   const double d_con_cfg = cfg.d_con;
-  fv3::launch3d(ctx, st, isc, iec + 1, jsc, jec + 1, 0, nz, FV_LAMBDA(int s, int i, int j, int k) {
+  fv3::launch3d(ctx, st, isc, iec + 1, jsc, jec + 1, 0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     const bool dc = d_con[k] > DCON_THRESHOLD;
     auto ubt = [&](int ii, int jj) {  // defined on [isc..iec] x [jsc..jec+1]
       const int64_t p = O3(s, ii, jj, k);
@@ -429,7 +436,7 @@ int fv3_d_sw(fv3_ctx *ctx, double *delpc, double *delp, double *pt, double *u, d
     if (d_con_cfg > DCON_THRESHOLD) heat_source[o] = heat_source[o] + hs;
   });
   // update_u_and_v (d_sw.py:582-608)
-  fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, 0, nz, FV_LAMBDA(int s, int i, int j, int k) {
+  fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, 0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     if (!(damp_vt[k] > 1e-5)) return;
     const int64_t o = O3(s, i, j, k);
     if (i <= iec) u[o] = u[o] + vt[o];

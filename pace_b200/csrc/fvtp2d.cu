@@ -6,6 +6,7 @@
 // 10 + (7 + 6*nmax) reference launches become 3 + (2 + nmax): the corner copies are index remaps at read time
 // (ppm.h), the Laplacian d2 of each del-n iteration is recomputed from the previous fluxes instead of stored.
 #include "common.h"
+#include "plane.h"
 #include "ppm.h"
 
 namespace {
@@ -39,7 +40,7 @@ void delnflux_core(const fv3_ctx *ctx, cudaStream_t st, const double *q, const d
   {
     double *fxo = bufx[0], *fyo = bufy[0];
     // d2_damp_interval / copy_stencil_interval + corner copies + fx/fy_calc_stencil_nord (delnflux.py:59-126,...)
-    fv3::launch3d(ctx, st, isc - nmax, iec + 2 + nmax, jsc - nmax, jec + 2 + nmax, 0, nk, FV_LAMBDA(int s, int i, int j, int k) {
+    fv3::launch3d(ctx, st, isc - nmax, iec + 2 + nmax, jsc - nmax, jec + 2 + nmax, 0, nk, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
       const bool hi = nord[k] > 0;
       const int r = hi ? nmax : 0;
       const double dk = copy_q ? 1.0 : damp[k];
@@ -64,7 +65,7 @@ void delnflux_core(const fv3_ctx *ctx, cudaStream_t st, const double *q, const d
     const double *fxo = bufx[cur], *fyo = bufy[cur];
     double *fxn = bufx[1 - cur], *fyn = bufy[1 - cur];
     // d2_highorder_stencil + corner copies + fx/fy_calc_stencil_column (delnflux.py:128-213)
-    fv3::launch3d(ctx, st, isc - nt, iec + 2 + nt, jsc - nt, jec + 2 + nt, 0, nk, FV_LAMBDA(int s, int i, int j, int k) {
+    fv3::launch3d(ctx, st, isc - nt, iec + 2 + nt, jsc - nt, jec + 2 + nt, 0, nk, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
       const bool hi = nord[k] > 0;
       const int64_t o = O3(s, i, j, k), o2 = O2(s, i, j);
       if (!hi) {  // level keeps its first-order fluxes
@@ -91,14 +92,14 @@ void delnflux_core(const fv3_ctx *ctx, cudaStream_t st, const double *q, const d
   }
   const double *fx2 = bufx[cur], *fy2 = bufy[cur];
   if (accumulate == 0) {
-    fv3::launch3d(ctx, st, isc - nmax, iec + 2 + nmax, jsc - nmax, jec + 2 + nmax, 0, nk, FV_LAMBDA(int s, int i, int j, int k) {
+    fv3::launch3d(ctx, st, isc - nmax, iec + 2 + nmax, jsc - nmax, jec + 2 + nmax, 0, nk, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
       const int64_t o = O3(s, i, j, k);
       out_fx[o] = fx2[o];
       out_fy[o] = fy2[o];
     });
   } else {
     // add_diffusive_component / diffusive_damp (delnflux.py:215-238) on the (nx+1) x (ny+1) interface domain
-    fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, 0, nk, FV_LAMBDA(int s, int i, int j, int k) {
+    fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, 0, nk, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
       const int64_t o = O3(s, i, j, k);
       if (accumulate == 1) {
         out_fx[o] = out_fx[o] + fx2[o];
@@ -109,6 +110,109 @@ void delnflux_core(const fv3_ctx *ctx, cudaStream_t st, const double *q, const d
       }
     });
   }
+}
+
+// ---- plane-resident transport (see plane.h) ------------------------------------------------------------------
+// Shared-memory planes (each PL = nj * sj doubles, same (i, j) offsets as a global plane):
+//   Q : q, cube corners filled for the y sweep, then for the x sweep; later q advected along y (q_i)
+//   A : inner y-sweep interface values (fy_in); finally the y flux
+//   B : inner x-sweep interface values (fx_in); finally the x flux
+//   D : q advected along x (q_j)
+struct PlaneArgs {
+  const double *q, *crx, *cry, *xfx, *yfx, *xu, *yu;
+};
+
+template <int MORD>
+FV_HD void fvtp2d_plane(const fv3_geom &g, const fv3_grid &m, int s, int k, const fv3::Block &b, const PlaneArgs &a,
+                        double *Q, double *A, double *B, double *D) {
+  const int sj = g.sj, h = g.halo;
+  const int isc = h, iec = h + g.nx - 1, jsc = h, jec = h + g.ny - 1, ied = iec + h, jed = jec + h;
+  const int64_t ob = O3(s, 0, 0, k), o2b = O2(s, 0, 0);
+  const double *q = a.q + ob, *crx = a.crx + ob, *cry = a.cry + ob, *xfx = a.xfx + ob, *yfx = a.yfx + ob;
+  const double *dxa = m.dxa + o2b, *dya = m.dya + o2b, *area = m.area + o2b;
+  const bool W = fv3::on_west(g, s), E = fv3::on_east(g, s), S = fv3::on_south(g, s), N = fv3::on_north(g, s);
+  const int nwi = ied + 1, nwj = jed + 1;
+  // 1. load q; 3x3 cube-corner halo blocks as copy_corners_y leaves them
+  b.par(nwi * nwj, [&](int t) {
+    const int j = t / nwi, i = t - j * nwi;
+    int ii = i, jj = j;
+    fv3::corner_y(g, s, ii, jj);
+    Q[j * sj + i] = q[jj * sj + ii];
+  });
+  // 2. inner y sweep on q: all columns, faces jsc .. jec+1
+  b.par(nwi * (g.ny + 1), [&](int t) {
+    const int jr = t / nwi, i = t - jr * nwi, j = jsc + jr, p = j * sj + i;
+    const fv3::Edge1D e{S, N, jsc, jec};
+    auto qy = [&](int jj) { return Q[jj * sj + i]; };
+    auto dy = [&](int jj) { return dya[jj * sj + i]; };
+    A[p] = fv3::ppm_flux_t<MORD>(qy, dy, cry[p], j, e);
+  });
+  // 3. cube-corner blocks as copy_corners_x leaves them
+  b.par(4 * h * h, [&](int t) {
+    const int c = t / (h * h), r = t - c * h * h, a1 = r / h, b1 = r - a1 * h;
+    const int i = (c & 1) ? iec + 1 + a1 : a1, j = (c & 2) ? jec + 1 + b1 : b1;
+    int ii = i, jj = j;
+    fv3::corner_x(g, s, ii, jj);
+    Q[j * sj + i] = q[jj * sj + ii];
+  });
+  // 4. inner x sweep on q: all rows, faces isc .. iec+1
+  b.par((g.nx + 1) * nwj, [&](int t) {
+    const int j = t / (g.nx + 1), i = isc + (t - j * (g.nx + 1)), p = j * sj + i;
+    const fv3::Edge1D e{W, E, isc, iec};
+    auto qx = [&](int ii) { return Q[j * sj + ii]; };
+    auto dx = [&](int ii) { return dxa[j * sj + ii]; };
+    B[p] = fv3::ppm_flux_t<MORD>(qx, dx, crx[p], i, e);
+  });
+  // 5. transverse updates: q_i (into Q, compute rows) and q_j (into D, compute columns)
+  b.par(nwi * nwj, [&](int t) {
+    const int j = t / nwi, i = t - j * nwi, p = j * sj + i;
+    const double qv = Q[p], ar = area[p];
+    if (j >= jsc && j <= jec) {
+      const double f0 = yfx[p] * A[p], f1 = yfx[p + sj] * A[p + sj];
+      Q[p] = (qv * ar + f0 - f1) / (ar + yfx[p] - yfx[p + sj]);
+    }
+    if (i >= isc && i <= iec) {
+      const double f0 = xfx[p] * B[p], f1 = xfx[p + 1] * B[p + 1];
+      D[p] = (qv * ar + f0 - f1) / (ar + xfx[p] - xfx[p + 1]);
+    }
+  });
+  // 6. outer sweeps and final fluxes (in place over the inner-sweep values)
+  const double *xu = a.xu + ob, *yu = a.yu + ob;
+  b.par((g.nx + 1) * (g.ny + 1), [&](int t) {
+    const int jr = t / (g.nx + 1), i = isc + (t - jr * (g.nx + 1)), j = jsc + jr, p = j * sj + i;
+    if (j <= jec) {
+      const fv3::Edge1D e{W, E, isc, iec};
+      auto qx = [&](int ii) { return Q[j * sj + ii]; };
+      auto dx = [&](int ii) { return dxa[j * sj + ii]; };
+      const double outer = fv3::ppm_flux_t<MORD>(qx, dx, crx[p], i, e);
+      B[p] = 0.5 * (outer + B[p]) * xu[p];
+    }
+    if (i <= iec) {
+      const fv3::Edge1D e{S, N, jsc, jec};
+      auto qy = [&](int jj) { return D[jj * sj + i]; };
+      auto dy = [&](int jj) { return dya[jj * sj + i]; };
+      const double outer = fv3::ppm_flux_t<MORD>(qy, dy, cry[p], j, e);
+      A[p] = 0.5 * (outer + A[p]) * yu[p];
+    }
+  });
+}
+
+template <int MORD>
+int fvtp2d_launch(const fv3_ctx *ctx, cudaStream_t st, PlaneArgs a, double *fx, double *fy, int nk) {
+  const fv3_geom g = ctx->g;
+  const fv3_grid m = ctx->m;
+  const int PL = g.nj * g.sj;
+  return fv3::launch_planes(ctx, st, 0, nk, 4 * PL, FV_LAMBDA(int s, int k, const fv3::Block &b) { FV_DEV_GM
+    double *Q = b.sm, *A = Q + PL, *B = A + PL, *D = B + PL;
+    fvtp2d_plane<MORD>(g, m, s, k, b, a, Q, A, B, D);
+    const int sj = g.sj, h = g.halo, nx1 = g.nx + 1;
+    const int64_t ob = O3(s, 0, 0, k);
+    b.par(nx1 * (g.ny + 1), [&](int t) {
+      const int jr = t / nx1, i = h + (t - jr * nx1), j = h + jr, p = j * sj + i;
+      if (jr < g.ny) fx[ob + p] = B[p];
+      if (i - h < g.nx) fy[ob + p] = A[p];
+    });
+  });
 }
 
 }  // namespace
@@ -134,67 +238,19 @@ int fv3_fvtp2d(fv3_ctx *ctx, const double *q, const double *crx, const double *c
   cudaStream_t st = (cudaStream_t)stream;
   const Idx x = make_idx(g);
   const int sj = g.sj;
-  const int isc = x.isc, iec = x.iec, jsc = x.jsc, jec = x.jec, ied = x.ied, jed = x.jed;
-  double *fy_in = fv3::scratch_field(ctx, S_FYIN), *fx_in = fv3::scratch_field(ctx, S_FXIN);
-  double *q_i = fv3::scratch_field(ctx, S_QI), *q_j = fv3::scratch_field(ctx, S_QJ);
-  const int ord_outer = hord, ord_inner = hord == 10 ? 8 : hord;
   const double *xu = x_mass_flux ? x_mass_flux : xfx, *yu = y_mass_flux ? y_mass_flux : yfx;
 
-  // KA: inner sweeps on q with the cube corners remapped (fvtp2d.py:290-291,305-306)
-  fv3::launch3d(ctx, st, 0, ied + 1, 0, jed + 1, 0, nk, FV_LAMBDA(int s, int i, int j, int k) {
-    const int64_t o = O3(s, i, j, k);
-    if (j >= jsc && j <= jec + 1) {
-      const fv3::Edge1D e{fv3::on_south(g, s), fv3::on_north(g, s), jsc, jec};
-      auto qy = [&](int jj) {
-        int ii = i, j2 = jj;
-        fv3::corner_y(g, s, ii, j2);
-        return q[O3(s, ii, j2, k)];
-      };
-      auto dy = [&](int jj) { return m.dya[O2(s, i, jj)]; };
-      fy_in[o] = fv3::ppm_flux(ord_inner, qy, dy, cry[o], j, e, true);
-    }
-    if (i >= isc && i <= iec + 1) {
-      const fv3::Edge1D e{fv3::on_west(g, s), fv3::on_east(g, s), isc, iec};
-      auto qx = [&](int ii) {
-        int i2 = ii, jj = j;
-        fv3::corner_x(g, s, i2, jj);
-        return q[O3(s, i2, jj, k)];
-      };
-      auto dx = [&](int ii) { return m.dxa[O2(s, ii, j)]; };
-      fx_in[o] = fv3::ppm_flux(ord_inner, qx, dx, crx[o], i, e, true);
-    }
-  });
-  // KB: q advected along y / along x (q_i_stencil, q_j_stencil; fvtp2d.py:33-63)
-  fv3::launch3d(ctx, st, 0, ied + 1, 0, jed + 1, 0, nk, FV_LAMBDA(int s, int i, int j, int k) {
-    const int64_t o = O3(s, i, j, k);
-    const double ar = m.area[O2(s, i, j)];
-    if (j >= jsc && j <= jec) {
-      const double f0 = yfx[o] * fy_in[o], f1 = yfx[o + sj] * fy_in[o + sj];
-      q_i[o] = (q[o] * ar + f0 - f1) / (ar + yfx[o] - yfx[o + sj]);
-    }
-    if (i >= isc && i <= iec) {
-      const double f0 = xfx[o] * fx_in[o], f1 = xfx[o + 1] * fx_in[o + 1];
-      q_j[o] = (q[o] * ar + f0 - f1) / (ar + xfx[o] - xfx[o + 1]);
-    }
-  });
-  // KC: outer sweeps and final fluxes (fvtp2d.py:66-93)
-  fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, 0, nk, FV_LAMBDA(int s, int i, int j, int k) {
-    const int64_t o = O3(s, i, j, k);
-    if (j <= jec) {
-      const fv3::Edge1D e{fv3::on_west(g, s), fv3::on_east(g, s), isc, iec};
-      auto qx = [&](int ii) { return q_i[O3(s, ii, j, k)]; };
-      auto dx = [&](int ii) { return m.dxa[O2(s, ii, j)]; };
-      const double outer = fv3::ppm_flux(ord_outer, qx, dx, crx[o], i, e, true);
-      fx[o] = 0.5 * (outer + fx_in[o]) * xu[o];
-    }
-    if (i <= iec) {
-      const fv3::Edge1D e{fv3::on_south(g, s), fv3::on_north(g, s), jsc, jec};
-      auto qy = [&](int jj) { return q_j[O3(s, i, jj, k)]; };
-      auto dy = [&](int jj) { return m.dya[O2(s, i, jj)]; };
-      const double outer = fv3::ppm_flux(ord_outer, qy, dy, cry[o], j, e, true);
-      fy[o] = 0.5 * (outer + fy_in[o]) * yu[o];
-    }
-  });
+  // inner sweeps, transverse updates, outer sweeps and final fluxes: ONE plane-resident kernel (fvtp2d.py:290-326)
+  const PlaneArgs pa{q, crx, cry, xfx, yfx, xu, yu};
+  const int mord = hord < 0 ? -hord : hord;
+  int rc;
+  if (mord == 8 || mord == 10)
+    rc = fvtp2d_launch<8>(ctx, st, pa, fx, fy, nk);
+  else if (mord == 5)
+    rc = fvtp2d_launch<5>(ctx, st, pa, fx, fy, nk);
+  else
+    rc = fvtp2d_launch<6>(ctx, st, pa, fx, fy, nk);
+  if (rc) return rc;
   if (damp_col != nullptr && nord_col != nullptr) {
     if (nmax > 2) {
       fv3::set_error("fv3_fvtp2d: nmax must be <= 2");
@@ -203,6 +259,57 @@ int fv3_fvtp2d(fv3_ctx *ctx, const double *q, const double *crx, const double *c
     delnflux_core(ctx, st, q, damp_col, nord_col, nmax, nk, mass != nullptr, fx, fy, mass ? 2 : 1, mass);
   }
   return fv3::check_launch("fv3_fvtp2d");
+}
+
+// ---- TracerAdvection sub-cycle, all tracers in one launch (tracer_2d_1l.py:341-392) --------------------------
+// Per plane: for every tracer, transport fluxes (hord_tr) stay in shared memory and are applied at once
+// (apply_tracer_flux :138-156); dp2 (apply_mass_flux :115-135) is evaluated on the fly; after the last tracer
+// dp2 is stored and, when another sub-cycle follows, swapped with dp1 (swap_dp :159-163).  Replaces
+// 1 + 2*nq launches and 9 field passes per tracer by 1 launch and 2 passes per tracer (+ the shared flux fields,
+// which stay L2-resident across the tracer loop).
+int fv3_tracer_subcycle(fv3_ctx *ctx, double *const *tracers, int nq, double *dp1, double *dp2, const double *mfx,
+                        const double *mfy, const double *cx, const double *cy, const double *xfx, const double *yfx,
+                        int hord, int swap, void *stream) {
+  const fv3_geom g = ctx->g;
+  const fv3_grid m = ctx->m;
+  const int mord = hord < 0 ? -hord : hord;
+  if (mord != 8) {
+    fv3::set_error("fv3_tracer_subcycle: only hord_tr = 8 is implemented");
+    return -1;
+  }
+  const int PL = g.nj * g.sj;
+  int rc = fv3::launch_planes(ctx, (cudaStream_t)stream, 0, g.nz, 4 * PL, FV_LAMBDA(int s, int k, const fv3::Block &b) { FV_DEV_GM
+    double *Q = b.sm, *A = Q + PL, *B = A + PL, *D = B + PL;
+    const int sj = g.sj, h = g.halo, nx = g.nx;
+    const int64_t ob = O3(s, 0, 0, k), o2b = O2(s, 0, 0);
+    const double *rarea = m.rarea + o2b;
+    for (int n = 0; n < nq; ++n) {
+      double *q = tracers[n];
+      const PlaneArgs pa{q, cx, cy, xfx, yfx, mfx, mfy};
+      fvtp2d_plane<8>(g, m, s, k, b, pa, Q, A, B, D);
+      b.par(nx * g.ny, [&](int t) {
+        const int jr = t / nx, p = (h + jr) * sj + h + (t - jr * nx);
+        const int64_t o = ob + p;
+        const double d1 = dp1[o];
+        const double d2 = d1 + (mfx[o] - mfx[o + 1] + mfy[o] - mfy[o + sj]) * rarea[p];
+        q[o] = (q[o] * d1 + (B[p] - B[p + 1] + A[p] - A[p + sj]) * rarea[p]) / d2;
+      });
+    }
+    b.par(nx * g.ny, [&](int t) {
+      const int jr = t / nx, p = (h + jr) * sj + h + (t - jr * nx);
+      const int64_t o = ob + p;
+      const double d1 = dp1[o];
+      const double d2 = d1 + (mfx[o] - mfx[o + 1] + mfy[o] - mfy[o + sj]) * rarea[p];
+      if (swap) {
+        dp1[o] = d2;
+        dp2[o] = d1;
+      } else {
+        dp2[o] = d2;
+      }
+    });
+  });
+  if (rc) return rc;
+  return fv3::check_launch("fv3_tracer_subcycle");
 }
 
 }  // extern "C"

@@ -23,7 +23,7 @@ int fv3_fv_prep(fv3_ctx *ctx, const double *uc, const double *vc, double *crx, d
   const int ied = iec + h, jed = jec + h;
 
   // KA: main_uc_vc_contra + uc_contra_y_edge + vc_contra_x_edge (fxadv.py:9-58,93-104)
-  fv3::launch3d(ctx, st, 0, ied + 1, 0, jed + 1, 0, nz, FV_LAMBDA(int s, int i, int j, int k) {
+  fv3::launch3d(ctx, st, 0, ied + 1, 0, jed + 1, 0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     const bool W = fv3::on_west(g, s), E = fv3::on_east(g, s), S = fv3::on_south(g, s), N = fv3::on_north(g, s);
     const int64_t o = O3(s, i, j, k), o2 = O2(s, i, j);
     if (i >= isc - 1 && i <= iec + 2) {
@@ -52,7 +52,7 @@ int fv3_fv_prep(fv3_ctx *ctx, const double *uc, const double *vc, double *crx, d
 
   // KB: vc_contra_y_edge (:61-90) on the two columns next to a west/east tile edge and
   //     uc_contra_x_edge (:107-133) on the two rows next to a south/north tile edge
-  fv3::launch3d(ctx, st, isc - 1, iec + 2, jsc - 1, jec + 2, 0, nz, FV_LAMBDA(int s, int i, int j, int k) {
+  fv3::launch3d(ctx, st, isc - 1, iec + 2, jsc - 1, jec + 2, 0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     const bool W = fv3::on_west(g, s), E = fv3::on_east(g, s), S = fv3::on_south(g, s), N = fv3::on_north(g, s);
     const int64_t o = O3(s, i, j, k), o2 = O2(s, i, j);
     const bool icol = (W && (i == isc - 1 || i == isc)) || (E && (i == iec || i == iec + 1));
@@ -74,7 +74,7 @@ int fv3_fv_prep(fv3_ctx *ctx, const double *uc, const double *vc, double *crx, d
   });
 
   // KC: uc_contra_corners (:136-243) and vc_contra_corners (:246-352): 16 points per subdomain and level
-  fv3::launch3d(ctx, st, 0, 16, 0, 1, 0, nz, FV_LAMBDA(int s, int id, int unused, int k) {
+  fv3::launch3d(ctx, st, 0, 16, 0, 1, 0, nz, FV_LAMBDA(int s, int id, int unused, int k) { FV_DEV_GM
     (void)unused;
     const bool W = fv3::on_west(g, s), E = fv3::on_east(g, s), S = fv3::on_south(g, s), N = fv3::on_north(g, s);
     const int which = id / 8;   // 0: uc_contra, 1: vc_contra
@@ -137,7 +137,7 @@ int fv3_fv_prep(fv3_ctx *ctx, const double *uc, const double *vc, double *crx, d
   });
 
   // KD: fxadv_fluxes_stencil (:355-390)
-  fv3::launch3d(ctx, st, 0, ied + 1, 0, jed + 1, 0, nz, FV_LAMBDA(int s, int i, int j, int k) {
+  fv3::launch3d(ctx, st, 0, ied + 1, 0, jed + 1, 0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     const int64_t o = O3(s, i, j, k), o2 = O2(s, i, j);
     if (i >= isc && i <= iec + 1) {
       const double a = ucc[o];

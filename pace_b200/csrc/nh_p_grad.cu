@@ -5,6 +5,7 @@
 //   fv3_apply_diffusive_heating <- apply_diffusive_heating (temperature_adjust.py:8-43)
 #include "a2b.h"
 #include "common.h"
+#include "plane.h"
 #include "ppm.h"
 
 extern "C" {
@@ -20,27 +21,43 @@ int fv3_nh_p_grad(fv3_ctx *ctx, double *u, double *v, double *pp, double *gz, do
   double *ppb = fv3::scratch_field(ctx, 16), *pk3b = fv3::scratch_field(ctx, 17), *gzb = fv3::scratch_field(ctx, 18);
   double *wk1 = fv3::scratch_field(ctx, 19);
   const double top_value = pow(ptop, akap);  // host libm, as `ptop ** akap` in the reference (:219)
-  // four A->B interpolations (nh_p_grad.py:221-224) + set_k0 (:11-20)
-  fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, 0, nz + 1, FV_LAMBDA(int s, int i, int j, int k) {
-    const int64_t o = O3(s, i, j, k);
-    auto qgz = [&](int ii, int jj) { return gz[O3(s, ii, jj, k)]; };
-    gzb[o] = fv3::a2b_point(g, m, s, qgz, i, j);
+  // four A->B interpolations (nh_p_grad.py:221-224) + set_k0 (:11-20): one plane-resident kernel per level
+  const int PL = g.nj * g.sj;
+  int rc = fv3::launch_planes(ctx, st, 0, nz + 1, 4 * PL, FV_LAMBDA(int s, int k, const fv3::Block &b) { FV_DEV_GM
+    double *SQ = b.sm, *QX = SQ + PL, *QY = QX + PL, *OUT = QY + PL;
+    const int64_t ob = O3(s, 0, 0, k);
+    const int sj2 = g.sj, nxc = g.nx + 1, nyc = g.ny + 1, h2 = g.halo;
+    auto store = [&](double *dst) {
+      b.par(nxc * nyc, [&](int t) {
+        const int jr = t / nxc, p = (h2 + jr) * sj2 + h2 + (t - jr * nxc);
+        dst[ob + p] = OUT[p];
+      });
+    };
+    auto fill = [&](double *dst, double value) {
+      b.par(nxc * nyc, [&](int t) {
+        const int jr = t / nxc, p = (h2 + jr) * sj2 + h2 + (t - jr * nxc);
+        dst[ob + p] = value;
+      });
+    };
+    fv3::a2b_plane(g, m, s, b, gz + ob, SQ, QX, QY, OUT);
+    store(gzb);
     if (k >= 1) {
-      auto qpp = [&](int ii, int jj) { return pp[O3(s, ii, jj, k)]; };
-      auto qpk = [&](int ii, int jj) { return pk3[O3(s, ii, jj, k)]; };
-      ppb[o] = fv3::a2b_point(g, m, s, qpp, i, j);
-      pk3b[o] = fv3::a2b_point(g, m, s, qpk, i, j);
+      fv3::a2b_plane(g, m, s, b, pp + ob, SQ, QX, QY, OUT);
+      store(ppb);
+      fv3::a2b_plane(g, m, s, b, pk3 + ob, SQ, QX, QY, OUT);
+      store(pk3b);
     } else {
-      ppb[o] = 0.0;
-      pk3b[o] = top_value;
+      fill(ppb, 0.0);
+      fill(pk3b, top_value);
     }
     if (k < nz) {
-      auto qdp = [&](int ii, int jj) { return delp[O3(s, ii, jj, k)]; };
-      wk1[o] = fv3::a2b_point(g, m, s, qdp, i, j);
+      fv3::a2b_plane(g, m, s, b, delp + ob, SQ, QX, QY, OUT);
+      store(wk1);
     }
   });
+  if (rc) return rc;
   // replace pp, pk3, gz by their B-grid values; calc_u / calc_v (:23-112)
-  fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, 0, nz + 1, FV_LAMBDA(int s, int i, int j, int k) {
+  fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, 0, nz + 1, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     const int64_t o = O3(s, i, j, k), o2 = O2(s, i, j);
     pp[o] = ppb[o];
     pk3[o] = pk3b[o];
@@ -72,7 +89,7 @@ int fv3_ray_fast(fv3_ctx *ctx, double *u, double *v, double *w, const double *rf
   const int isc = h, iec = h + g.nx - 1, jsc = h, jec = h + g.ny - 1;
   const double *dp = m.dp_ref;
   const int hydrostatic = ctx->c.hydrostatic;
-  fv3::launch2d(ctx, (cudaStream_t)stream, isc, iec + 2, jsc, jec + 2, FV_LAMBDA(int s, int i, int j) {
+  fv3::launch2d(ctx, (cudaStream_t)stream, isc, iec + 2, jsc, jec + 2, FV_LAMBDA(int s, int i, int j) { FV_DEV_GM
     const int64_t c0 = O3(s, i, j, 0), sk = g.sk;
     auto damp = [&](double *q) {
       double dm = 0.0;
@@ -106,7 +123,7 @@ int fv3_del2cubed(fv3_ctx *ctx, double *qdel, double cd, int nmax, int nk, void 
     const int nt = ntimes - (n + 1);
     const double *qo = bufs[cur];
     double *qn = bufs[1 - cur];
-    fv3::launch3d(ctx, st, isc - nt, iec + 1 + nt, jsc - nt, jec + 1 + nt, 0, nk, FV_LAMBDA(int s, int i, int j, int k) {
+    fv3::launch3d(ctx, st, isc - nt, iec + 1 + nt, jsc - nt, jec + 1 + nt, 0, nk, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
       const bool W = fv3::on_west(g, s), E = fv3::on_east(g, s), S = fv3::on_south(g, s), N = fv3::on_north(g, s);
       const double third = 1.0 / 3.0;
       auto q0 = [&](int ii, int jj) { return qo[O3(s, ii, jj, k)]; };
@@ -151,7 +168,7 @@ int fv3_del2cubed(fv3_ctx *ctx, double *qdel, double cd, int nmax, int nk, void 
     cur = 1 - cur;
   }
   if (cur == 1) {
-    fv3::launch3d(ctx, st, isc, iec + 1, jsc, jec + 1, 0, nk, FV_LAMBDA(int s, int i, int j, int k) {
+    fv3::launch3d(ctx, st, isc, iec + 1, jsc, jec + 1, 0, nk, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
       const int64_t o = O3(s, i, j, k);
       qdel[o] = tmp[o];
     });
@@ -164,7 +181,7 @@ int fv3_apply_diffusive_heating(fv3_ctx *ctx, const double *delp, const double *
   const fv3_geom g = ctx->g;
   const int h = g.halo;
   const double RDG = -287.05 / 9.80665, CV_AIR = 1004.6 - 287.05;
-  fv3::launch3d(ctx, (cudaStream_t)stream, h, h + g.nx, h, h + g.ny, 0, nk, FV_LAMBDA(int s, int i, int j, int k) {
+  fv3::launch3d(ctx, (cudaStream_t)stream, h, h + g.nx, h, h + g.ny, 0, nk, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     const int64_t o = O3(s, i, j, k);
     const double cp = cappa[o];
     const double pkz = pow(RDG * delp[o] / delz[o] * pt[o], cp / (1.0 - cp));

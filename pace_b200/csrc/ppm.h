@@ -157,6 +157,24 @@ FV_HD double ppm_flux8(Q q, DX dx, double c, int i, const Edge1D &e, bool minmax
   return q(i) + (1.0 + c) * (bl + c * b0);
 }
 
+// Same value as ppm_flux8, with the upwind cell selected first so that the (large) bl/br code exists once.
+template <class Q, class DX>
+FV_HD double ppm_flux8_upwind(Q q, DX dx, double c, int i, const Edge1D &e, bool minmax) {
+  const bool pos = c > 0.0;
+  const int cc = pos ? i - 1 : i;
+  double bl, br;
+  ppm_blbr8(q, dx, cc, e, minmax, bl, br);
+  const double b0 = bl + br;
+  return pos ? q(cc) + (1.0 - c) * (br - c * b0) : q(cc) + (1.0 + c) * (bl + c * b0);
+}
+
+// compile-time order: MORD = |hord| in {5, 6, 8}
+template <int MORD, class Q, class DX>
+FV_HD double ppm_flux_t(Q q, DX dx, double c, int i, const Edge1D &e) {
+  if (MORD < 8) return ppm_flux_lt8(MORD, q, dx, c, i, e);
+  return ppm_flux8_upwind(q, dx, c, i, e, true);
+}
+
 template <class Q, class DX>
 FV_HD double ppm_flux(int ord, Q q, DX dx, double c, int i, const Edge1D &e, bool minmax) {
   const int mord = ord < 0 ? -ord : ord;

@@ -195,7 +195,7 @@ int fv3_map_single(fv3_ctx *ctx, double *q1, const double *pe1, const double *pe
     return -1;
   }
   const int h = g.halo, km = g.nz;
-  fv3::launch2d(ctx, (cudaStream_t)stream, h, h + g.nx + i_extra, h, h + g.ny + j_extra, FV_LAMBDA(int s, int i, int j) {
+  fv3::launch2d(ctx, (cudaStream_t)stream, h, h + g.nx + i_extra, h, h + g.ny + j_extra, FV_LAMBDA(int s, int i, int j) { FV_DEV_GM
     const int64_t c0 = O3(s, i, j, 0), sk = g.sk;
     Profile p;
     double dp1[NKMAX], p1[NKMAX];
@@ -240,7 +240,7 @@ int fv3_map_single(fv3_ctx *ctx, double *q1, const double *pe1, const double *pe
 int fv3_fillz(fv3_ctx *ctx, double *const *tracers, int nq, const double *dp2, void *stream) {
   const fv3_geom g = ctx->g;
   const int h = g.halo, km = g.nz;
-  fv3::launch3d(ctx, (cudaStream_t)stream, h, h + g.nx, h, h + g.ny, 0, nq, FV_LAMBDA(int s, int i, int j, int t) {
+  fv3::launch3d(ctx, (cudaStream_t)stream, h, h + g.nx, h, h + g.ny, 0, nq, FV_LAMBDA(int s, int i, int j, int t) { FV_DEV_GM
     double *qf = tracers[t];
     const int64_t c0 = O3(s, i, j, 0), sk = g.sk;
     double q[NKMAX], dp[NKMAX], lower_fix[NKMAX], upper_fix[NKMAX], dm[NKMAX], dm_pos[NKMAX];
@@ -324,7 +324,7 @@ int fv3_remap_prep(fv3_ctx *ctx, double *const *tracers6, double *q_con, double 
   const fv3_geom g = ctx->g;
   const fv3_grid m = ctx->m;
   const int h = g.halo, km = g.nz;
-  fv3::launch2d(ctx, (cudaStream_t)stream, h, h + g.nx, h, h + g.ny + 1, FV_LAMBDA(int s, int i, int j) {
+  fv3::launch2d(ctx, (cudaStream_t)stream, h, h + g.nx, h, h + g.ny + 1, FV_LAMBDA(int s, int i, int j) { FV_DEV_GM
     const int64_t c0 = O3(s, i, j, 0), sk = g.sk;
     // init_pe on the (nx, ny+1) domain
     for (int k = 0; k <= km; ++k) pe1[c0 + k * sk] = pe[c0 + k * sk];
@@ -363,7 +363,7 @@ int fv3_remap_post(fv3_ctx *ctx, double *const *tracers6, double *q_con, double 
                    void *stream) {
   const fv3_geom g = ctx->g;
   const int h = g.halo, km = g.nz;
-  fv3::launch3d(ctx, (cudaStream_t)stream, h, h + g.nx, h, h + g.ny, 0, km + 1, FV_LAMBDA(int s, int i, int j, int k) {
+  fv3::launch3d(ctx, (cudaStream_t)stream, h, h + g.nx, h, h + g.ny, 0, km + 1, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     const int64_t o = O3(s, i, j, k);
     pe0[o] = peln[o];
     peln[o] = pn2[o];
@@ -386,7 +386,7 @@ int fv3_remap_pressures(fv3_ctx *ctx, const double *pe, double *pe0, double *pe3
   const fv3_grid m = ctx->m;
   const int h = g.halo, km = g.nz;
   const int64_t off = dir == 0 ? g.sj : 1;
-  fv3::launch3d(ctx, (cudaStream_t)stream, h, h + g.nx + (dir == 1), h, h + g.ny + (dir == 0), 0, km + 1, FV_LAMBDA(int s, int i, int j, int k) {
+  fv3::launch3d(ctx, (cudaStream_t)stream, h, h + g.nx + (dir == 1), h, h + g.ny + (dir == 0), 0, km + 1, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     const int64_t o = O3(s, i, j, k), ob = O3(s, i, j, km);
     const double bkh = 0.5 * m.bk[k];
     if (k == 0) {
@@ -404,7 +404,7 @@ int fv3_remap_finish(fv3_ctx *ctx, double *const *tracers6, const double *pe2, d
                      int last_step, double dtmp, double r_vir, void *stream) {
   const fv3_geom g = ctx->g;
   const int h = g.halo, km = g.nz;
-  fv3::launch3d(ctx, (cudaStream_t)stream, h, h + g.nx, h, h + g.ny, 0, km, FV_LAMBDA(int s, int i, int j, int k) {
+  fv3::launch3d(ctx, (cudaStream_t)stream, h, h + g.nx, h, h + g.ny, 0, km, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     const int64_t o = O3(s, i, j, k);
     if (k >= 1) pe[o] = pe2[o];
     if (last_step) {
@@ -422,7 +422,7 @@ int fv3_fv_setup(fv3_ctx *ctx, double *const *tracers6, double *q_con, double *c
                  double *cappa, const double *delp, const double *delz, double *dp1, void *stream) {
   const fv3_geom g = ctx->g;
   const int h = g.halo;
-  fv3::launch3d(ctx, (cudaStream_t)stream, h, h + g.nx, h, h + g.ny, 0, g.nz, FV_LAMBDA(int s, int i, int j, int k) {
+  fv3::launch3d(ctx, (cudaStream_t)stream, h, h + g.nx, h, h + g.ny, 0, g.nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     const int64_t o = O3(s, i, j, k);
     double cvm, qc;
     moist_cv(tracers6[0][o], tracers6[1][o], tracers6[2][o], tracers6[3][o], tracers6[4][o], tracers6[5][o], cvm, qc);
@@ -443,7 +443,7 @@ int fv3_fv_setup(fv3_ctx *ctx, double *const *tracers6, double *q_con, double *c
 int fv3_omega_from_w(fv3_ctx *ctx, const double *delp, const double *delz, const double *w, double *omga, void *stream) {
   const fv3_geom g = ctx->g;
   const int h = g.halo;
-  fv3::launch3d(ctx, (cudaStream_t)stream, h, h + g.nx, h, h + g.ny, 0, g.nz, FV_LAMBDA(int s, int i, int j, int k) {
+  fv3::launch3d(ctx, (cudaStream_t)stream, h, h + g.nx, h, h + g.ny, 0, g.nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     const int64_t o = O3(s, i, j, k);
     omga[o] = delp[o] / delz[o] * w[o];
   });

@@ -15,7 +15,7 @@ int fv3_tracer_flux_prep(fv3_ctx *ctx, double *cxd, double *cyd, double *mfxd, d
   const int h = g.halo, sj = g.sj;
   const int isc = h, iec = h + g.nx - 1, jsc = h, jec = h + g.ny - 1;
   const double frac = 1.0 / n_split;
-  fv3::launch3d(ctx, (cudaStream_t)stream, 0, g.ni, 0, g.nj, 0, g.nz, FV_LAMBDA(int s, int i, int j, int k) {
+  fv3::launch3d(ctx, (cudaStream_t)stream, 0, g.ni, 0, g.nj, 0, g.nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     const int64_t o = O3(s, i, j, k), o2 = O2(s, i, j);
     if (i >= isc && i <= iec + 1 && j >= jsc - 3 && j <= jec + 3) {
       const double cx = cxd[o];
@@ -42,7 +42,7 @@ int fv3_tracer_apply_mass_flux(fv3_ctx *ctx, const double *dp1, const double *mf
   const fv3_geom g = ctx->g;
   const fv3_grid m = ctx->m;
   const int h = g.halo, sj = g.sj;
-  fv3::launch3d(ctx, (cudaStream_t)stream, h, h + g.nx, h, h + g.ny, 0, g.nz, FV_LAMBDA(int s, int i, int j, int k) {
+  fv3::launch3d(ctx, (cudaStream_t)stream, h, h + g.nx, h, h + g.ny, 0, g.nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     const int64_t o = O3(s, i, j, k);
     dp2[o] = dp1[o] + (mfx[o] - mfx[o + 1] + mfy[o] - mfy[o + sj]) * m.rarea[O2(s, i, j)];
   });
@@ -54,7 +54,7 @@ int fv3_tracer_apply_flux(fv3_ctx *ctx, double *q, const double *dp1, const doub
   const fv3_geom g = ctx->g;
   const fv3_grid m = ctx->m;
   const int h = g.halo, sj = g.sj;
-  fv3::launch3d(ctx, (cudaStream_t)stream, h, h + g.nx, h, h + g.ny, 0, g.nz, FV_LAMBDA(int s, int i, int j, int k) {
+  fv3::launch3d(ctx, (cudaStream_t)stream, h, h + g.nx, h, h + g.ny, 0, g.nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     const int64_t o = O3(s, i, j, k);
     q[o] = (q[o] * dp1[o] + (fx[o] - fx[o + 1] + fy[o] - fy[o + sj]) * m.rarea[O2(s, i, j)]) / dp2[o];
   });
@@ -64,7 +64,7 @@ int fv3_tracer_apply_flux(fv3_ctx *ctx, double *q, const double *dp1, const doub
 int fv3_tracer_swap_dp(fv3_ctx *ctx, double *dp1, double *dp2, void *stream) {
   const fv3_geom g = ctx->g;
   const int h = g.halo;
-  fv3::launch3d(ctx, (cudaStream_t)stream, h, h + g.nx, h, h + g.ny, 0, g.nz, FV_LAMBDA(int s, int i, int j, int k) {
+  fv3::launch3d(ctx, (cudaStream_t)stream, h, h + g.nx, h, h + g.ny, 0, g.nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     const int64_t o = O3(s, i, j, k);
     const double t = dp1[o];
     dp1[o] = dp2[o];
@@ -84,7 +84,7 @@ int fv3_c2l_ord4(fv3_ctx *ctx, const double *u, const double *v, double *ua, dou
   const int h = g.halo, sj = g.sj;
   const int isc = h, iec = h + g.nx - 1, jsc = h, jec = h + g.ny - 1;
   const double C1 = 1.125, C2 = -0.125;
-  fv3::launch3d(ctx, (cudaStream_t)stream, isc, iec + 1, jsc, jec + 1, 0, g.nz, FV_LAMBDA(int s, int i, int j, int k) {
+  fv3::launch3d(ctx, (cudaStream_t)stream, isc, iec + 1, jsc, jec + 1, 0, g.nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     const bool W = fv3::on_west(g, s), E = fv3::on_east(g, s), S = fv3::on_south(g, s), N = fv3::on_north(g, s);
     const int64_t o = O3(s, i, j, k), o2 = O2(s, i, j);
     double utmp, vtmp;

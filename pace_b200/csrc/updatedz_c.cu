@@ -47,7 +47,7 @@ int fv3_update_dz_c(fv3_ctx *ctx, const double *zs, const double *ut, const doub
   const int isc = h, iec = h + g.nx - 1, jsc = h, jec = h + g.ny - 1;
   double *gzn = fv3::scratch_field(ctx, 0);
   const double *dp0 = m.dp_ref;
-  fv3::launch3d(ctx, st, isc - 1, iec + 2, jsc - 1, jec + 2, 0, nz + 1, FV_LAMBDA(int s, int i, int j, int k) {
+  fv3::launch3d(ctx, st, isc - 1, iec + 2, jsc - 1, jec + 2, 0, nz + 1, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     // pressure-weighted interpolation of the layer fluxes to interface k (updatedzc.py:15-33,91-100)
     auto iface = [&](const double *vel, int64_t ocol) {
       if (k == 0) {
@@ -80,7 +80,7 @@ int fv3_update_dz_c(fv3_ctx *ctx, const double *zs, const double *ut, const doub
     const int64_t o = c0 + (int64_t)k * g.sk;
     gzn[o] = (gz[o] * ar + fx0 - fx1 + fy0 - fy1) / (ar + xfx0 - xfx1 + yfx0 - yfx1);
   });
-  fv3::launch2d(ctx, st, isc - 1, iec + 2, jsc - 1, jec + 2, FV_LAMBDA(int s, int i, int j) {
+  fv3::launch2d(ctx, st, isc - 1, iec + 2, jsc - 1, jec + 2, FV_LAMBDA(int s, int i, int j) { FV_DEV_GM
     const int64_t c0 = O3(s, i, j, 0);
     const double rdt = 1.0 / dt;
     double below = gzn[c0 + (int64_t)nz * g.sk];
@@ -100,7 +100,7 @@ int fv3_p_grad_c(fv3_ctx *ctx, const double *rdxc, const double *rdyc, double *u
   const fv3_geom g = ctx->g;
   const int h = g.halo, sj = g.sj;
   const int64_t sk = g.sk;
-  fv3::launch3d(ctx, (cudaStream_t)stream, h, h + g.nx + 1, h, h + g.ny + 1, 0, g.nz, FV_LAMBDA(int s, int i, int j, int k) {
+  fv3::launch3d(ctx, (cudaStream_t)stream, h, h + g.nx + 1, h, h + g.ny + 1, 0, g.nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     const int64_t o = O3(s, i, j, k), o2 = O2(s, i, j);
     uc[o] = uc[o] + dt2 * rdxc[o2] / (delpc[o - 1] + delpc[o]) *
                         ((gz[o - 1 + sk] - gz[o]) * (pkc[o + sk] - pkc[o - 1]) + (gz[o - 1] - gz[o + sk]) * (pkc[o - 1 + sk] - pkc[o]));
@@ -114,7 +114,7 @@ int fv3_p_grad_c(fv3_ctx *ctx, const double *rdxc, const double *rdyc, double *u
 int fv3_gz_from_delz(fv3_ctx *ctx, const double *zs, const double *delz, double *gz, void *stream) {
   const fv3_geom g = ctx->g;
   const int h = g.halo, nz = g.nz;
-  fv3::launch2d(ctx, (cudaStream_t)stream, h, h + g.nx, h, h + g.ny, FV_LAMBDA(int s, int i, int j) {
+  fv3::launch2d(ctx, (cudaStream_t)stream, h, h + g.nx, h, h + g.ny, FV_LAMBDA(int s, int i, int j) { FV_DEV_GM
     const int64_t c0 = O3(s, i, j, 0);
     double v = zs[O2(s, i, j)];
     gz[c0 + (int64_t)nz * g.sk] = v;
@@ -130,7 +130,7 @@ int fv3_gz_from_delz(fv3_ctx *ctx, const double *zs, const double *delz, double 
 int fv3_pem_from_delp(fv3_ctx *ctx, const double *delp, double *pem, double ptop, void *stream) {
   const fv3_geom g = ctx->g;
   const int h = g.halo, nz = g.nz;
-  fv3::launch2d(ctx, (cudaStream_t)stream, h - 1, h + g.nx + 1, h - 1, h + g.ny + 1, FV_LAMBDA(int s, int i, int j) {
+  fv3::launch2d(ctx, (cudaStream_t)stream, h - 1, h + g.nx + 1, h - 1, h + g.ny + 1, FV_LAMBDA(int s, int i, int j) { FV_DEV_GM
     const int64_t c0 = O3(s, i, j, 0);
     double v = ptop;
     pem[c0] = v;
@@ -146,7 +146,7 @@ int fv3_pem_from_delp(fv3_ctx *ctx, const double *delp, double *pem, double ptop
 int fv3_compute_geopotential(fv3_ctx *ctx, const double *zh, double *gz, void *stream) {
   const fv3_geom g = ctx->g;
   const int h = g.halo;
-  fv3::launch3d(ctx, (cudaStream_t)stream, h - 2, h + g.nx + 2, h - 2, h + g.ny + 2, 0, g.nz + 1, FV_LAMBDA(int s, int i, int j, int k) {
+  fv3::launch3d(ctx, (cudaStream_t)stream, h - 2, h + g.nx + 2, h - 2, h + g.ny + 2, 0, g.nz + 1, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     const int64_t o = O3(s, i, j, k);
     gz[o] = zh[o] * 9.80665;
   });

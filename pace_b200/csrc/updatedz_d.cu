@@ -32,7 +32,7 @@ int fv3_update_dz_d(fv3_ctx *ctx, const double *surface_height, double *height, 
   double *fx = fv3::scratch_field(ctx, 20), *fy = fv3::scratch_field(ctx, 21);
   double *gx = fv3::scratch_field(ctx, 22), *gy = fv3::scratch_field(ctx, 23);
   // cubic_spline_interpolation_from_layer_center_to_interfaces (updatedzd.py:157-196), 4 fields, full domain
-  fv3::launch3d(ctx, st, 0, ied + 1, 0, jed + 1, 0, 4, FV_LAMBDA(int s, int i, int j, int f) {
+  fv3::launch3d(ctx, st, 0, ied + 1, 0, jed + 1, 0, 4, FV_LAMBDA(int s, int i, int j, int f) { FV_DEV_GM
     const double *qc = f == 0 ? crx : (f == 1 ? xfx : (f == 2 ? cry : yfx));
     double *qi = f == 0 ? crx_i : (f == 1 ? xfx_i : (f == 2 ? cry_i : yfx_i));
     const int64_t c0 = O3(s, i, j, 0), sk = g.sk;
@@ -61,7 +61,7 @@ int fv3_update_dz_d(fv3_ctx *ctx, const double *surface_height, double *height, 
     return rc;
   if ((rc = fv3_delnflux_nosg(ctx, height, gx, gy, damp_col, nord_col, nmax, nz + 1, stream))) return rc;
   // apply_height_fluxes (updatedzd.py:70-126): compute domain, BACKWARD monotonicity fix
-  fv3::launch2d(ctx, st, isc, iec + 1, jsc, jec + 1, FV_LAMBDA(int s, int i, int j) {
+  fv3::launch2d(ctx, st, isc, iec + 1, jsc, jec + 1, FV_LAMBDA(int s, int i, int j) { FV_DEV_GM
     const int64_t c0 = O3(s, i, j, 0), sk = g.sk;
     const double ar = m.area[O2(s, i, j)];
     double below = 0.0;

@@ -23,6 +23,10 @@ class TracerAdvection:
         spec = qf.get_quantity_halo_spec(_C3, n_halo=3)
         self._updater = comm.get_scalar_halo_updater([spec] * self._tracer_count)
         self._tracer_list = list(tracers.values())
+        import torch
+
+        self._tracer_ptrs = torch.tensor([q.ptr for q in self._tracer_list], dtype=torch.int64).to(self._rt.device)
+        self._fused = abs(transport._hord) == 8
 
     def __call__(self, tracers: Dict[str, Quantity], dp1: Quantity, x_mass_flux: Quantity, y_mass_flux: Quantity,
                  x_courant: Quantity, y_courant: Quantity):
@@ -35,6 +39,16 @@ class TracerAdvection:
         qs = list(tracers.values())
         self._updater.update(qs)
         dp2 = self._tmp_dp
+        if self._fused and [q.ptr for q in qs] == [q.ptr for q in self._tracer_list]:
+            # one launch per sub-cycle for all tracers (fluxes never leave shared memory)
+            for it in range(n_split):
+                last_call = it == n_split - 1
+                rt.call("fv3_tracer_subcycle", self._tracer_ptrs.data_ptr(), len(qs), dp1.ptr, dp2.ptr, x_mass_flux.ptr,
+                        y_mass_flux.ptr, x_courant.ptr, y_courant.ptr, self._x_area_flux.ptr, self._y_area_flux.ptr,
+                        int(self.finite_volume_transport._hord), 0 if last_call else 1)
+                if not last_call:
+                    self._updater.update(qs)
+            return
         for it in range(n_split):
             last_call = it == n_split - 1
             rt.call("fv3_tracer_apply_mass_flux", dp1.ptr, x_mass_flux.ptr, y_mass_flux.ptr, dp2.ptr)
