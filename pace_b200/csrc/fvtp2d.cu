@@ -118,34 +118,44 @@ void delnflux_core(const fv3_ctx *ctx, cudaStream_t st, const double *q, const d
 //   A : inner y-sweep interface values (fy_in); finally the y flux
 //   B : inner x-sweep interface values (fx_in); finally the x flux
 //   D : q advected along x (q_j)
+//   T : per-sweep staging: PPM edge values al (hord 5/6) or limited slopes dm (hord 8), computed once per line
+constexpr int FVTP_PLANES = 5;
 struct PlaneArgs {
   const double *q, *crx, *cry, *xfx, *yfx, *xu, *yu;
 };
 
 template <int MORD>
 FV_HD void fvtp2d_plane(const fv3_geom &g, const fv3_grid &m, int s, int k, const fv3::Block &b, const PlaneArgs &a,
-                        double *Q, double *A, double *B, double *D) {
-  const int sj = g.sj, h = g.halo;
-  const int isc = h, iec = h + g.nx - 1, jsc = h, jec = h + g.ny - 1, ied = iec + h, jed = jec + h;
+                        double *Q, double *A, double *B, double *D, double *T) {
+  const int sj = g.sj, h = g.halo, nx = g.nx, ny = g.ny;
+  const int isc = h, iec = h + nx - 1, jsc = h, jec = h + ny - 1, ied = iec + h, jed = jec + h;
   const int64_t ob = O3(s, 0, 0, k), o2b = O2(s, 0, 0);
   const double *q = a.q + ob, *crx = a.crx + ob, *cry = a.cry + ob, *xfx = a.xfx + ob, *yfx = a.yfx + ob;
   const double *dxa = m.dxa + o2b, *dya = m.dya + o2b, *area = m.area + o2b;
-  const bool W = fv3::on_west(g, s), E = fv3::on_east(g, s), S = fv3::on_south(g, s), N = fv3::on_north(g, s);
+  const fv3::Edge1D ex{fv3::on_west(g, s), fv3::on_east(g, s), isc, iec};
+  const fv3::Edge1D ey{fv3::on_south(g, s), fv3::on_north(g, s), jsc, jec};
   const int nwi = ied + 1, nwj = jed + 1;
+  // staging ranges: al on faces start-1 .. end+2, dm on cells start-2 .. end+2
+  const int st0 = MORD < 8 ? -1 : -2, stn = MORD < 8 ? 4 : 5;
   // 1. load q; 3x3 cube-corner halo blocks as copy_corners_y leaves them
-  b.par(nwi * nwj, [&](int t) {
-    const int j = t / nwi, i = t - j * nwi;
+  b.par2(nwi, nwj, [&](int i, int j) {
     int ii = i, jj = j;
     fv3::corner_y(g, s, ii, jj);
     Q[j * sj + i] = q[jj * sj + ii];
   });
   // 2. inner y sweep on q: all columns, faces jsc .. jec+1
-  b.par(nwi * (g.ny + 1), [&](int t) {
-    const int jr = t / nwi, i = t - jr * nwi, j = jsc + jr, p = j * sj + i;
-    const fv3::Edge1D e{S, N, jsc, jec};
+  b.par2(nwi, ny + stn, [&](int i, int jr) {
+    const int j = jsc + st0 + jr;
     auto qy = [&](int jj) { return Q[jj * sj + i]; };
     auto dy = [&](int jj) { return dya[jj * sj + i]; };
-    A[p] = fv3::ppm_flux_t<MORD>(qy, dy, cry[p], j, e);
+    T[j * sj + i] = fv3::ppm_stage<MORD>(qy, dy, j, ey);
+  });
+  b.par2(nwi, ny + 1, [&](int i, int jr) {
+    const int j = jsc + jr, p = j * sj + i;
+    auto qy = [&](int jj) { return Q[jj * sj + i]; };
+    auto ty = [&](int jj) { return T[jj * sj + i]; };
+    auto dy = [&](int jj) { return dya[jj * sj + i]; };
+    A[p] = fv3::ppm_flux_staged<MORD>(qy, ty, dy, cry[p], j, ey);
   });
   // 3. cube-corner blocks as copy_corners_x leaves them
   b.par(4 * h * h, [&](int t) {
@@ -156,16 +166,22 @@ FV_HD void fvtp2d_plane(const fv3_geom &g, const fv3_grid &m, int s, int k, cons
     Q[j * sj + i] = q[jj * sj + ii];
   });
   // 4. inner x sweep on q: all rows, faces isc .. iec+1
-  b.par((g.nx + 1) * nwj, [&](int t) {
-    const int j = t / (g.nx + 1), i = isc + (t - j * (g.nx + 1)), p = j * sj + i;
-    const fv3::Edge1D e{W, E, isc, iec};
+  b.par2(nx + stn, nwj, [&](int ir, int j) {
+    const int i = isc + st0 + ir;
     auto qx = [&](int ii) { return Q[j * sj + ii]; };
     auto dx = [&](int ii) { return dxa[j * sj + ii]; };
-    B[p] = fv3::ppm_flux_t<MORD>(qx, dx, crx[p], i, e);
+    T[j * sj + i] = fv3::ppm_stage<MORD>(qx, dx, i, ex);
+  });
+  b.par2(nx + 1, nwj, [&](int ir, int j) {
+    const int i = isc + ir, p = j * sj + i;
+    auto qx = [&](int ii) { return Q[j * sj + ii]; };
+    auto tx = [&](int ii) { return T[j * sj + ii]; };
+    auto dx = [&](int ii) { return dxa[j * sj + ii]; };
+    B[p] = fv3::ppm_flux_staged<MORD>(qx, tx, dx, crx[p], i, ex);
   });
   // 5. transverse updates: q_i (into Q, compute rows) and q_j (into D, compute columns)
-  b.par(nwi * nwj, [&](int t) {
-    const int j = t / nwi, i = t - j * nwi, p = j * sj + i;
+  b.par2(nwi, nwj, [&](int i, int j) {
+    const int p = j * sj + i;
     const double qv = Q[p], ar = area[p];
     if (j >= jsc && j <= jec) {
       const double f0 = yfx[p] * A[p], f1 = yfx[p + sj] * A[p + sj];
@@ -176,24 +192,36 @@ FV_HD void fvtp2d_plane(const fv3_geom &g, const fv3_grid &m, int s, int k, cons
       D[p] = (qv * ar + f0 - f1) / (ar + xfx[p] - xfx[p + 1]);
     }
   });
-  // 6. outer sweeps and final fluxes (in place over the inner-sweep values)
+  // 6. outer x sweep on q_i (compute rows) -> x flux, in place over fx_in
   const double *xu = a.xu + ob, *yu = a.yu + ob;
-  b.par((g.nx + 1) * (g.ny + 1), [&](int t) {
-    const int jr = t / (g.nx + 1), i = isc + (t - jr * (g.nx + 1)), j = jsc + jr, p = j * sj + i;
-    if (j <= jec) {
-      const fv3::Edge1D e{W, E, isc, iec};
-      auto qx = [&](int ii) { return Q[j * sj + ii]; };
-      auto dx = [&](int ii) { return dxa[j * sj + ii]; };
-      const double outer = fv3::ppm_flux_t<MORD>(qx, dx, crx[p], i, e);
-      B[p] = 0.5 * (outer + B[p]) * xu[p];
-    }
-    if (i <= iec) {
-      const fv3::Edge1D e{S, N, jsc, jec};
-      auto qy = [&](int jj) { return D[jj * sj + i]; };
-      auto dy = [&](int jj) { return dya[jj * sj + i]; };
-      const double outer = fv3::ppm_flux_t<MORD>(qy, dy, cry[p], j, e);
-      A[p] = 0.5 * (outer + A[p]) * yu[p];
-    }
+  b.par2(nx + stn, ny, [&](int ir, int jr) {
+    const int i = isc + st0 + ir, j = jsc + jr;
+    auto qx = [&](int ii) { return Q[j * sj + ii]; };
+    auto dx = [&](int ii) { return dxa[j * sj + ii]; };
+    T[j * sj + i] = fv3::ppm_stage<MORD>(qx, dx, i, ex);
+  });
+  b.par2(nx + 1, ny, [&](int ir, int jr) {
+    const int i = isc + ir, j = jsc + jr, p = j * sj + i;
+    auto qx = [&](int ii) { return Q[j * sj + ii]; };
+    auto tx = [&](int ii) { return T[j * sj + ii]; };
+    auto dx = [&](int ii) { return dxa[j * sj + ii]; };
+    const double outer = fv3::ppm_flux_staged<MORD>(qx, tx, dx, crx[p], i, ex);
+    B[p] = 0.5 * (outer + B[p]) * xu[p];
+  });
+  // 7. outer y sweep on q_j (compute columns) -> y flux, in place over fy_in
+  b.par2(nx, ny + stn, [&](int ir, int jr) {
+    const int i = isc + ir, j = jsc + st0 + jr;
+    auto qy = [&](int jj) { return D[jj * sj + i]; };
+    auto dy = [&](int jj) { return dya[jj * sj + i]; };
+    T[j * sj + i] = fv3::ppm_stage<MORD>(qy, dy, j, ey);
+  });
+  b.par2(nx, ny + 1, [&](int ir, int jr) {
+    const int i = isc + ir, j = jsc + jr, p = j * sj + i;
+    auto qy = [&](int jj) { return D[jj * sj + i]; };
+    auto ty = [&](int jj) { return T[jj * sj + i]; };
+    auto dy = [&](int jj) { return dya[jj * sj + i]; };
+    const double outer = fv3::ppm_flux_staged<MORD>(qy, ty, dy, cry[p], j, ey);
+    A[p] = 0.5 * (outer + A[p]) * yu[p];
   });
 }
 
@@ -202,9 +230,9 @@ int fvtp2d_launch(const fv3_ctx *ctx, cudaStream_t st, PlaneArgs a, double *fx, 
   const fv3_geom g = ctx->g;
   const fv3_grid m = ctx->m;
   const int PL = g.nj * g.sj;
-  return fv3::launch_planes(ctx, st, 0, nk, 4 * PL, FV_LAMBDA(int s, int k, const fv3::Block &b) { FV_DEV_GM
-    double *Q = b.sm, *A = Q + PL, *B = A + PL, *D = B + PL;
-    fvtp2d_plane<MORD>(g, m, s, k, b, a, Q, A, B, D);
+  return fv3::launch_planes(ctx, st, 0, nk, FVTP_PLANES * PL, FV_LAMBDA(int s, int k, const fv3::Block &b) { FV_DEV_GM
+    double *Q = b.sm, *A = Q + PL, *B = A + PL, *D = B + PL, *T = D + PL;
+    fvtp2d_plane<MORD>(g, m, s, k, b, a, Q, A, B, D, T);
     const int sj = g.sj, h = g.halo, nx1 = g.nx + 1;
     const int64_t ob = O3(s, 0, 0, k);
     b.par(nx1 * (g.ny + 1), [&](int t) {
@@ -278,15 +306,15 @@ int fv3_tracer_subcycle(fv3_ctx *ctx, double *const *tracers, int nq, double *dp
     return -1;
   }
   const int PL = g.nj * g.sj;
-  int rc = fv3::launch_planes(ctx, (cudaStream_t)stream, 0, g.nz, 4 * PL, FV_LAMBDA(int s, int k, const fv3::Block &b) { FV_DEV_GM
-    double *Q = b.sm, *A = Q + PL, *B = A + PL, *D = B + PL;
+  int rc = fv3::launch_planes(ctx, (cudaStream_t)stream, 0, g.nz, FVTP_PLANES * PL, FV_LAMBDA(int s, int k, const fv3::Block &b) { FV_DEV_GM
+    double *Q = b.sm, *A = Q + PL, *B = A + PL, *D = B + PL, *T = D + PL;
     const int sj = g.sj, h = g.halo, nx = g.nx;
     const int64_t ob = O3(s, 0, 0, k), o2b = O2(s, 0, 0);
     const double *rarea = m.rarea + o2b;
     for (int n = 0; n < nq; ++n) {
       double *q = tracers[n];
       const PlaneArgs pa{q, cx, cy, xfx, yfx, mfx, mfy};
-      fvtp2d_plane<8>(g, m, s, k, b, pa, Q, A, B, D);
+      fvtp2d_plane<8>(g, m, s, k, b, pa, Q, A, B, D, T);
       b.par(nx * g.ny, [&](int t) {
         const int jr = t / nx, p = (h + jr) * sj + h + (t - jr * nx);
         const int64_t o = ob + p;

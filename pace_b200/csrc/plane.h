@@ -14,7 +14,7 @@
 
 namespace fv3 {
 
-constexpr int PLANE_THREADS = 512;
+constexpr int PLANE_THREADS = 1024;
 
 struct Block {
   double *sm;
@@ -23,10 +23,28 @@ struct Block {
   void par(int n, F f) const {
     for (int t = 0; t < n; ++t) f(t);
   }
+  // f(ir, jr) for ir in [0, w), jr in [0, nrows)
+  template <class F>
+  void par2(int w, int nrows, F f) const {
+    for (int jr = 0; jr < nrows; ++jr)
+      for (int ir = 0; ir < w; ++ir) f(ir, jr);
+  }
 #else
   template <class F>
   __device__ __forceinline__ void par(int n, F f) const {
     for (int t = threadIdx.x; t < n; t += blockDim.x) f(t);
+    __syncthreads();
+  }
+  // row-major (ir fastest) over w x nrows points; the row index comes from a float reciprocal (exact for the
+  // plane sizes that fit in shared memory: t < 2^20, w < 2^10) instead of an integer division per point
+  template <class F>
+  __device__ __forceinline__ void par2(int w, int nrows, F f) const {
+    const int n = w * nrows;
+    const float inv = 1.0f / (float)w;
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+      const int jr = (int)(((float)t + 0.5f) * inv);
+      f(t - jr * w, jr);
+    }
     __syncthreads();
   }
 #endif

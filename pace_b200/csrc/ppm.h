@@ -175,6 +175,51 @@ FV_HD double ppm_flux_t(Q q, DX dx, double c, int i, const Edge1D &e) {
   return ppm_flux8_upwind(q, dx, c, i, e, true);
 }
 
+// ---- two-pass form used by the plane-resident kernels: pass 1 stores, per line, the edge values al (MORD < 8) or
+// the limited slopes dm (MORD == 8) ONCE per face / cell; pass 2 builds the interface value from them.  Same
+// expressions as ppm_flux_lt8 / ppm_blbr8, so the result is bit-identical to the one-pass form.
+template <int MORD, class Q, class DX>
+FV_HD double ppm_stage(Q q, DX dx, int i, const Edge1D &e) {
+  if (MORD < 8) return ppm_al_lt8(q, dx, i, e);
+  return ppm_dm8(q, i);
+}
+// T: accessor of the staged values (al at face i / dm of cell i)
+template <int MORD, class Q, class T, class DX>
+FV_HD double ppm_flux_staged(Q q, T t, DX dx, double c, int i, const Edge1D &e) {
+  if (MORD < 8) {
+    const double al0 = t(i - 1), al1 = t(i), al2 = t(i + 1);
+    const double ql = q(i - 1), qr = q(i);
+    const double bl_l = al0 - ql, br_l = al1 - ql, b0_l = bl_l + br_l;
+    const double bl_r = al1 - qr, br_r = al2 - qr, b0_r = bl_r + br_r;
+    bool s_l, s_r;
+    if (MORD == 5) {
+      s_l = bl_l * br_l < 0;
+      s_r = bl_r * br_r < 0;
+    } else {
+      s_l = (3.0 * fabs(b0_l)) < fabs(bl_l - br_l);
+      s_r = (3.0 * fabs(b0_r)) < fabs(bl_r - br_r);
+    }
+    const double mask = (s_l || s_r) ? 1.0 : 0.0;
+    const double fx1 = ppm_fx1(c, br_l, b0_l, bl_r, b0_r);
+    return c > 0.0 ? ql + fx1 * mask : qr + fx1 * mask;
+  }
+  const bool pos = c > 0.0;
+  const int cc = pos ? i - 1 : i;
+  const double qc = q(cc);
+  double bl, br;
+  if ((e.lo && cc >= e.start - 1 && cc <= e.start + 1) || (e.hi && cc >= e.end - 1 && cc <= e.end + 1)) {
+    ppm_blbr8(q, dx, cc, e, true, bl, br);
+  } else {
+    const double dm0 = t(cc), xt = 2.0 * dm0;
+    const double alc = 0.5 * (q(cc - 1) + qc) + 1.0 / 3.0 * (t(cc - 1) - dm0);
+    const double alr = 0.5 * (qc + q(cc + 1)) + 1.0 / 3.0 * (dm0 - t(cc + 1));
+    bl = -1.0 * rsign(dmin(fabs(xt), fabs(alc - qc)), xt);
+    br = rsign(dmin(fabs(xt), fabs(alr - qc)), xt);
+  }
+  const double b0 = bl + br;
+  return pos ? qc + (1.0 - c) * (br - c * b0) : qc + (1.0 + c) * (bl + c * b0);
+}
+
 template <class Q, class DX>
 FV_HD double ppm_flux(int ord, Q q, DX dx, double c, int i, const Edge1D &e, bool minmax) {
   const int mord = ord < 0 ? -ord : ord;
