@@ -202,22 +202,32 @@ void divergence_damping(fv3_ctx *ctx, cudaStream_t st, const double *u, const do
     dd8 = pow(base, (double)(nord + 1));
   }
   // a2b_ord4 of the relative vorticity + Smagorinsky-type diffusion + high-order damping
-  // (divergence_damping.py:590-632)
-  fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, k0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
-    const int64_t o = O3(s, i, j, k);
-    double vo;
-    if (dddmp < 1e-5) {
-      vo = 0.0;
-    } else {
-      auto q = [&](int ii, int jj) { return vort_a[O3(s, ii, jj, k)]; };
-      const double vb = fv3::a2b_point(g, m, s, q, i, j);
-      const double dp = delpc[o];
-      vo = absdt * sqrt(dp * dp + vb * vb);
-    }
-    const double damp = da_min_c * fv3::dmax(d2_bg[k], fv3::dmin(0.2, dddmp * fabs(vo)));
-    vo = damp * delpc[o] + dd8 * divg_d[o];
-    vort_b[o] = vo;
-    ke[o] = ke[o] + vo;
+  // (divergence_damping.py:590-632): one plane-resident kernel, the B-grid vorticity never leaves shared memory
+  const int PL = g.nj * g.sj;
+  fv3::launch_planes(ctx, st, k0, nz, 4 * PL, FV_LAMBDA(int s, int k, const fv3::Block &b) { FV_DEV_GM
+    double *SQ = b.sm, *QX = SQ + PL, *QY = QX + PL, *OUT = QY + PL;
+    const int64_t ob = O3(s, 0, 0, k);
+    const bool smag = !(dddmp < 1e-5);
+    if (smag) fv3::a2b_plane(g, m, s, b, vort_a + ob, SQ, QX, QY, OUT);
+    const int sj2 = g.sj, h2 = g.halo;
+    const double *rarea_unused = nullptr;
+    (void)rarea_unused;
+    b.par2(g.nx + 1, g.ny + 1, [&](int ir, int jr) {
+      const int p = (h2 + jr) * sj2 + h2 + ir;
+      const int64_t o = ob + p;
+      double vo;
+      if (!smag) {
+        vo = 0.0;
+      } else {
+        const double vb = OUT[p];
+        const double dp = delpc[o];
+        vo = absdt * sqrt(dp * dp + vb * vb);
+      }
+      const double damp = da_min_c * fv3::dmax(d2_bg[k], fv3::dmin(0.2, dddmp * fabs(vo)));
+      vo = damp * delpc[o] + dd8 * divg_d[o];
+      vort_b[o] = vo;
+      ke[o] = ke[o] + vo;
+    });
   });
 }
 

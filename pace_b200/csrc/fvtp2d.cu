@@ -27,91 +27,6 @@ Idx make_idx(const fv3_geom &g) {
   return x;
 }
 
-// accumulate: 0 = leave fx2/fy2 in (out_fx, out_fy); 1 = out_fx += fx2 ; 2 = out_fx += 0.5*damp*(mass[-1]+mass)*fx2
-void delnflux_core(const fv3_ctx *ctx, cudaStream_t st, const double *q, const double *damp, const double *nord,
-                   int nmax, int nk, bool copy_q, double *out_fx, double *out_fy, int accumulate, const double *mass) {
-  const fv3_geom g = ctx->g;
-  const fv3_grid m = ctx->m;
-  const Idx x = make_idx(g);
-  const int sj = g.sj;
-  double *bufx[2] = {fv3::scratch_field(ctx, S_DA), fv3::scratch_field(ctx, S_DA + 2)};
-  double *bufy[2] = {fv3::scratch_field(ctx, S_DA + 1), fv3::scratch_field(ctx, S_DA + 3)};
-  const int isc = x.isc, iec = x.iec, jsc = x.jsc, jec = x.jec;
-  {
-    double *fxo = bufx[0], *fyo = bufy[0];
-    // d2_damp_interval / copy_stencil_interval + corner copies + fx/fy_calc_stencil_nord (delnflux.py:59-126,...)
-    fv3::launch3d(ctx, st, isc - nmax, iec + 2 + nmax, jsc - nmax, jec + 2 + nmax, 0, nk, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
-      const bool hi = nord[k] > 0;
-      const int r = hi ? nmax : 0;
-      const double dk = copy_q ? 1.0 : damp[k];
-      auto d2x = [&](int ii, int jj) {
-        if (hi) fv3::corner_x(g, s, ii, jj);
-        const double v = q[O3(s, ii, jj, k)];
-        return copy_q ? v : dk * v;
-      };
-      auto d2y = [&](int ii, int jj) {
-        if (hi) fv3::corner_y(g, s, ii, jj);
-        const double v = q[O3(s, ii, jj, k)];
-        return copy_q ? v : dk * v;
-      };
-      const int64_t o = O3(s, i, j, k), o2 = O2(s, i, j);
-      if (i >= isc - r && i <= iec + 1 + r && j >= jsc - r && j <= jec + r) fxo[o] = m.del6_v[o2] * (d2x(i - 1, j) - d2x(i, j));
-      if (i >= isc - r && i <= iec + r && j >= jsc - r && j <= jec + 1 + r) fyo[o] = m.del6_u[o2] * (d2y(i, j - 1) - d2y(i, j));
-    });
-  }
-  int cur = 0;
-  for (int n = 0; n < nmax; ++n) {
-    const int nt = nmax - 1 - n;
-    const double *fxo = bufx[cur], *fyo = bufy[cur];
-    double *fxn = bufx[1 - cur], *fyn = bufy[1 - cur];
-    // d2_highorder_stencil + corner copies + fx/fy_calc_stencil_column (delnflux.py:128-213)
-    fv3::launch3d(ctx, st, isc - nt, iec + 2 + nt, jsc - nt, jec + 2 + nt, 0, nk, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
-      const bool hi = nord[k] > 0;
-      const int64_t o = O3(s, i, j, k), o2 = O2(s, i, j);
-      if (!hi) {  // level keeps its first-order fluxes
-        if (i >= isc && i <= iec + 1 && j >= jsc && j <= jec) fxn[o] = fxo[o];
-        if (i >= isc && i <= iec && j >= jsc && j <= jec + 1) fyn[o] = fyo[o];
-        return;
-      }
-      auto d2 = [&](int ii, int jj) {
-        const int64_t p = O3(s, ii, jj, k);
-        return (fxo[p] - fxo[p + 1] + fyo[p] - fyo[p + sj]) * m.rarea[O2(s, ii, jj)];
-      };
-      auto d2x = [&](int ii, int jj) {
-        fv3::corner_x(g, s, ii, jj);
-        return d2(ii, jj);
-      };
-      auto d2y = [&](int ii, int jj) {
-        fv3::corner_y(g, s, ii, jj);
-        return d2(ii, jj);
-      };
-      if (i <= iec + 1 + nt && j <= jec + nt) fxn[o] = -m.del6_v[o2] * (d2x(i - 1, j) - d2x(i, j));
-      if (i <= iec + nt && j <= jec + 1 + nt) fyn[o] = -m.del6_u[o2] * (d2y(i, j - 1) - d2y(i, j));
-    });
-    cur = 1 - cur;
-  }
-  const double *fx2 = bufx[cur], *fy2 = bufy[cur];
-  if (accumulate == 0) {
-    fv3::launch3d(ctx, st, isc - nmax, iec + 2 + nmax, jsc - nmax, jec + 2 + nmax, 0, nk, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
-      const int64_t o = O3(s, i, j, k);
-      out_fx[o] = fx2[o];
-      out_fy[o] = fy2[o];
-    });
-  } else {
-    // add_diffusive_component / diffusive_damp (delnflux.py:215-238) on the (nx+1) x (ny+1) interface domain
-    fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, 0, nk, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
-      const int64_t o = O3(s, i, j, k);
-      if (accumulate == 1) {
-        out_fx[o] = out_fx[o] + fx2[o];
-        out_fy[o] = out_fy[o] + fy2[o];
-      } else {
-        out_fx[o] = out_fx[o] + 0.5 * damp[k] * (mass[o - 1] + mass[o]) * fx2[o];
-        out_fy[o] = out_fy[o] + 0.5 * damp[k] * (mass[o - sj] + mass[o]) * fy2[o];
-      }
-    });
-  }
-}
-
 // ---- plane-resident transport (see plane.h) ------------------------------------------------------------------
 // Shared-memory planes (each PL = nj * sj doubles, same (i, j) offsets as a global plane):
 //   Q : q, cube corners filled for the y sweep, then for the x sweep; later q advected along y (q_i)
@@ -225,20 +140,90 @@ FV_HD void fvtp2d_plane(const fv3_geom &g, const fv3_grid &m, int s, int k, cons
   });
 }
 
+// ---- plane-resident del-n fluxes (DelnFlux / DelnFluxNoSG, delnflux.py:59-238,1164-1261) ------------------------
+// D2: the field being differenced (damp * q, then the Laplacians of the previous fluxes), FX / FY: its fluxes.
+// All nord iterations run in shared memory; on return FX / FY hold fx2 / fy2 on the interface domain
+// [isc..iec+1] x [jsc..jec(+1)].  q points at the global (s, k) plane.
+FV_HD void delnflux_plane(const fv3_geom &g, const fv3_grid &m, int s, const fv3::Block &b, const double *q, double dk,
+                          bool hi, int nmax, bool copy_q, double *D2, double *FX, double *FY) {
+  const int sj = g.sj, h = g.halo, nx = g.nx, ny = g.ny;
+  const int isc = h, jsc = h;
+  const int64_t o2b = O2(s, 0, 0);
+  const double *del6_u = m.del6_u + o2b, *del6_v = m.del6_v + o2b, *rarea = m.rarea + o2b;
+  const int r = hi ? nmax : 0;
+  // d2 = damp * q on cells [isc-r-1 .. iec+1+r] x [jsc-r-1 .. jec+1+r]
+  b.par2(nx + 2 * r + 2, ny + 2 * r + 2, [&](int ir, int jr) {
+    const int p = (jsc - r - 1 + jr) * sj + isc - r - 1 + ir;
+    const double v = q[p];
+    D2[p] = copy_q ? v : dk * v;
+  });
+  auto d2x = [&](int ii, int jj) {
+    if (hi) fv3::corner_x(g, s, ii, jj);
+    return D2[jj * sj + ii];
+  };
+  auto d2y = [&](int ii, int jj) {
+    if (hi) fv3::corner_y(g, s, ii, jj);
+    return D2[jj * sj + ii];
+  };
+  b.par2(nx + 2 * r + 1, ny + 2 * r + 1, [&](int ir, int jr) {
+    const int i = isc - r + ir, j = jsc - r + jr, p = j * sj + i;
+    if (jr < ny + 2 * r) FX[p] = del6_v[p] * (d2x(i - 1, j) - d2x(i, j));
+    if (ir < nx + 2 * r) FY[p] = del6_u[p] * (d2y(i, j - 1) - d2y(i, j));
+  });
+  if (!hi) return;
+  for (int n = 0; n < nmax; ++n) {
+    const int nt = nmax - 1 - n;
+    b.par2(nx + 2 * nt + 2, ny + 2 * nt + 2, [&](int ir, int jr) {
+      const int p = (jsc - nt - 1 + jr) * sj + isc - nt - 1 + ir;
+      D2[p] = (FX[p] - FX[p + 1] + FY[p] - FY[p + sj]) * rarea[p];
+    });
+    b.par2(nx + 2 * nt + 1, ny + 2 * nt + 1, [&](int ir, int jr) {
+      const int i = isc - nt + ir, j = jsc - nt + jr, p = j * sj + i;
+      int ia = i - 1, ja = j, ib = i, jb = j;
+      fv3::corner_x(g, s, ia, ja);
+      fv3::corner_x(g, s, ib, jb);
+      if (jr < ny + 2 * nt) FX[p] = -del6_v[p] * (D2[ja * sj + ia] - D2[jb * sj + ib]);
+      ia = i, ja = j - 1, ib = i, jb = j;
+      fv3::corner_y(g, s, ia, ja);
+      fv3::corner_y(g, s, ib, jb);
+      if (ir < nx + 2 * nt) FY[p] = -del6_u[p] * (D2[ja * sj + ia] - D2[jb * sj + ib]);
+    });
+  }
+}
+
+// mode: 0 = transport fluxes only; 1 = fx += fx2 (DelnFlux without mass); 2 = fx += 0.5*damp*(mass[-1]+mass)*fx2
 template <int MORD>
-int fvtp2d_launch(const fv3_ctx *ctx, cudaStream_t st, PlaneArgs a, double *fx, double *fy, int nk) {
+int fvtp2d_launch(const fv3_ctx *ctx, cudaStream_t st, PlaneArgs a, double *fx, double *fy, int nk, int mode,
+                  const double *damp, const double *nord, int nmax, const double *mass) {
   const fv3_geom g = ctx->g;
   const fv3_grid m = ctx->m;
   const int PL = g.nj * g.sj;
   return fv3::launch_planes(ctx, st, 0, nk, FVTP_PLANES * PL, FV_LAMBDA(int s, int k, const fv3::Block &b) { FV_DEV_GM
     double *Q = b.sm, *A = Q + PL, *B = A + PL, *D = B + PL, *T = D + PL;
     fvtp2d_plane<MORD>(g, m, s, k, b, a, Q, A, B, D, T);
-    const int sj = g.sj, h = g.halo, nx1 = g.nx + 1;
+    const int sj = g.sj, h = g.halo, nx = g.nx, ny = g.ny;
     const int64_t ob = O3(s, 0, 0, k);
-    b.par(nx1 * (g.ny + 1), [&](int t) {
-      const int jr = t / nx1, i = h + (t - jr * nx1), j = h + jr, p = j * sj + i;
-      if (jr < g.ny) fx[ob + p] = B[p];
-      if (i - h < g.nx) fy[ob + p] = A[p];
+    if (mode == 0) {
+      b.par2(nx + 1, ny + 1, [&](int ir, int jr) {
+        const int p = (h + jr) * sj + h + ir;
+        if (jr < ny) fx[ob + p] = B[p];
+        if (ir < nx) fy[ob + p] = A[p];
+      });
+      return;
+    }
+    // del-n damping fluxes of q, added to the transport fluxes (delnflux.py:1164-1207, 215-238)
+    const double dk = damp[k];
+    delnflux_plane(g, m, s, b, a.q + ob, dk, nord[k] > 0, nmax, mode == 2, Q, D, T);
+    const double *ms = mass + ob;
+    b.par2(nx + 1, ny + 1, [&](int ir, int jr) {
+      const int p = (h + jr) * sj + h + ir;
+      if (mode == 1) {
+        if (jr < ny) fx[ob + p] = B[p] + D[p];
+        if (ir < nx) fy[ob + p] = A[p] + T[p];
+      } else {
+        if (jr < ny) fx[ob + p] = B[p] + 0.5 * dk * (ms[p - 1] + ms[p]) * D[p];
+        if (ir < nx) fy[ob + p] = A[p] + 0.5 * dk * (ms[p - sj] + ms[p]) * T[p];
+      }
     });
   });
 }
@@ -253,7 +238,21 @@ int fv3_delnflux_nosg(fv3_ctx *ctx, const double *q, double *fx2, double *fy2, c
     fv3::set_error("fv3_delnflux_nosg: nmax must be 0..2 (halo 3)");
     return -1;
   }
-  delnflux_core(ctx, (cudaStream_t)stream, q, damp_col, nord_col, nmax, nk, false, fx2, fy2, 0, nullptr);
+  const fv3_geom g = ctx->g;
+  const fv3_grid m = ctx->m;
+  const int PL = g.nj * g.sj;
+  int rc = fv3::launch_planes(ctx, (cudaStream_t)stream, 0, nk, 3 * PL, FV_LAMBDA(int s, int k, const fv3::Block &b) { FV_DEV_GM
+    double *D2 = b.sm, *FX = D2 + PL, *FY = FX + PL;
+    const int64_t ob = O3(s, 0, 0, k);
+    delnflux_plane(g, m, s, b, q + ob, damp_col[k], nord_col[k] > 0, nmax, false, D2, FX, FY);
+    const int sj = g.sj, h = g.halo, nx = g.nx, ny = g.ny;
+    b.par2(nx + 1, ny + 1, [&](int ir, int jr) {
+      const int p = (h + jr) * sj + h + ir;
+      if (jr < ny) fx2[ob + p] = FX[p];
+      if (ir < nx) fy2[ob + p] = FY[p];
+    });
+  });
+  if (rc) return rc;
   return fv3::check_launch("fv3_delnflux_nosg");
 }
 
@@ -261,31 +260,30 @@ int fv3_fvtp2d(fv3_ctx *ctx, const double *q, const double *crx, const double *c
                const double *yfx, double *fx, double *fy, const double *x_mass_flux, const double *y_mass_flux,
                const double *mass, int hord, const double *nord_col, const double *damp_col, int nmax, int nk,
                void *stream) {
-  const fv3_geom g = ctx->g;
-  const fv3_grid m = ctx->m;
   cudaStream_t st = (cudaStream_t)stream;
-  const Idx x = make_idx(g);
-  const int sj = g.sj;
   const double *xu = x_mass_flux ? x_mass_flux : xfx, *yu = y_mass_flux ? y_mass_flux : yfx;
 
-  // inner sweeps, transverse updates, outer sweeps and final fluxes: ONE plane-resident kernel (fvtp2d.py:290-326)
+  // inner sweeps, transverse updates, outer sweeps, final fluxes and (optionally) the del-n damping fluxes:
+  // ONE plane-resident kernel (fvtp2d.py:290-346)
   const PlaneArgs pa{q, crx, cry, xfx, yfx, xu, yu};
   const int mord = hord < 0 ? -hord : hord;
-  int rc;
-  if (mord == 8 || mord == 10)
-    rc = fvtp2d_launch<8>(ctx, st, pa, fx, fy, nk);
-  else if (mord == 5)
-    rc = fvtp2d_launch<5>(ctx, st, pa, fx, fy, nk);
-  else
-    rc = fvtp2d_launch<6>(ctx, st, pa, fx, fy, nk);
-  if (rc) return rc;
+  int mode = 0;
   if (damp_col != nullptr && nord_col != nullptr) {
     if (nmax > 2) {
       fv3::set_error("fv3_fvtp2d: nmax must be <= 2");
       return -1;
     }
-    delnflux_core(ctx, st, q, damp_col, nord_col, nmax, nk, mass != nullptr, fx, fy, mass ? 2 : 1, mass);
+    mode = mass ? 2 : 1;
   }
+  const double *ms = mass ? mass : q;
+  int rc;
+  if (mord == 8 || mord == 10)
+    rc = fvtp2d_launch<8>(ctx, st, pa, fx, fy, nk, mode, damp_col, nord_col, nmax, ms);
+  else if (mord == 5)
+    rc = fvtp2d_launch<5>(ctx, st, pa, fx, fy, nk, mode, damp_col, nord_col, nmax, ms);
+  else
+    rc = fvtp2d_launch<6>(ctx, st, pa, fx, fy, nk, mode, damp_col, nord_col, nmax, ms);
+  if (rc) return rc;
   return fv3::check_launch("fv3_fvtp2d");
 }
 
