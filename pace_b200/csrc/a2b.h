@@ -147,7 +147,7 @@ FV_HD double a2b_point(const fv3_geom &g, const fv3_grid &m, int s, Q q, int i, 
 //   SQ: qin plane   QX / QY: ppm_volume_mean_x / _y   OUT: B-grid result (tile-edge values first, then the rest)
 // qin / qout are global pointers to the start of the (s, k) plane; each array holds nj * sj doubles.
 template <class B>
-FV_HD void a2b_plane(const fv3_geom &g, const fv3_grid &m, int s, const B &b, const double *qin, double *SQ, double *QX,
+FV_DEV void a2b_plane(const fv3_geom &g, const fv3_grid &m, int s, const B &b, const double *qin, double *SQ, double *QX,
                      double *QY, double *OUT) {
   const int sj = g.sj, h = g.halo;
   const int isc = h, iec = h + g.nx - 1, jsc = h, jec = h + g.ny - 1;

@@ -15,11 +15,13 @@
 #ifdef FV3_HOSTSIM
 typedef void *cudaStream_t;
 #define FV_HD inline
+#define FV_DEV inline
 #define FV_LAMBDA [=]
 #define FV_RESTRICT
 #else
 #include <cuda_runtime.h>
 #define FV_HD __host__ __device__ __forceinline__
+#define FV_DEV __device__ __forceinline__
 #define FV_LAMBDA [=] __device__
 #define FV_RESTRICT __restrict__
 #endif

@@ -40,7 +40,7 @@ struct PlaneArgs {
 };
 
 template <int MORD>
-FV_HD void fvtp2d_plane(const fv3_geom &g, const fv3_grid &m, int s, int k, const fv3::Block &b, const PlaneArgs &a,
+FV_DEV void fvtp2d_plane(const fv3_geom &g, const fv3_grid &m, int s, int k, const fv3::Block &b, const PlaneArgs &a,
                         double *Q, double *A, double *B, double *D, double *T) {
   const int sj = g.sj, h = g.halo, nx = g.nx, ny = g.ny;
   const int isc = h, iec = h + nx - 1, jsc = h, jec = h + ny - 1, ied = iec + h, jed = jec + h;
@@ -144,7 +144,7 @@ FV_HD void fvtp2d_plane(const fv3_geom &g, const fv3_grid &m, int s, int k, cons
 // D2: the field being differenced (damp * q, then the Laplacians of the previous fluxes), FX / FY: its fluxes.
 // All nord iterations run in shared memory; on return FX / FY hold fx2 / fy2 on the interface domain
 // [isc..iec+1] x [jsc..jec(+1)].  q points at the global (s, k) plane.
-FV_HD void delnflux_plane(const fv3_geom &g, const fv3_grid &m, int s, const fv3::Block &b, const double *q, double dk,
+FV_DEV void delnflux_plane(const fv3_geom &g, const fv3_grid &m, int s, const fv3::Block &b, const double *q, double dk,
                           bool hi, int nmax, bool copy_q, double *D2, double *FX, double *FY) {
   const int sj = g.sj, h = g.halo, nx = g.nx, ny = g.ny;
   const int isc = h, jsc = h;
