@@ -16,12 +16,14 @@
 typedef void *cudaStream_t;
 #define FV_HD inline
 #define FV_DEV inline
+#define FV_LDG(ptr) (*(ptr))
 #define FV_LAMBDA [=]
 #define FV_RESTRICT
 #else
 #include <cuda_runtime.h>
 #define FV_HD __host__ __device__ __forceinline__
 #define FV_DEV __device__ __forceinline__
+#define FV_LDG(ptr) __ldg(ptr)  // read-only global operand: LDG.NC, free to be hoisted above shared-memory traffic
 #define FV_LAMBDA [=] __device__
 #define FV_RESTRICT __restrict__
 #endif

@@ -53,11 +53,11 @@ FV_DEV void fvtp2d_plane(const fv3_geom &g, const fv3_grid &m, int s, int k, con
   // staging ranges: al on faces start-1 .. end+2, dm on cells start-2 .. end+2
   const int st0 = MORD < 8 ? -1 : -2, stn = MORD < 8 ? 4 : 5;
   // 1. load q; 3x3 cube-corner halo blocks as copy_corners_y leaves them
-  b.par2(nwi, nwj, [&](int i, int j) {
+  b.par2_pre<1>(nwi, nwj, [&](int i, int j, double *v) {
     int ii = i, jj = j;
     fv3::corner_y(g, s, ii, jj);
-    Q[j * sj + i] = q[jj * sj + ii];
-  });
+    v[0] = FV_LDG(q + jj * sj + ii);
+  }, [&](int i, int j, const double *v) { Q[j * sj + i] = v[0]; });
   // 2. inner y sweep on q: all columns, faces jsc .. jec+1
   b.par2(nwi, ny + stn, [&](int i, int jr) {
     const int j = jsc + st0 + jr;
@@ -65,12 +65,13 @@ FV_DEV void fvtp2d_plane(const fv3_geom &g, const fv3_grid &m, int s, int k, con
     auto dy = [&](int jj) { return dya[jj * sj + i]; };
     T[j * sj + i] = fv3::ppm_stage<MORD>(qy, dy, j, ey);
   });
-  b.par2(nwi, ny + 1, [&](int i, int jr) {
+  b.par2_pre<1>(nwi, ny + 1, [&](int i, int jr, double *v) { v[0] = FV_LDG(cry + (jsc + jr) * sj + i); },
+                [&](int i, int jr, const double *v) {
     const int j = jsc + jr, p = j * sj + i;
     auto qy = [&](int jj) { return Q[jj * sj + i]; };
     auto ty = [&](int jj) { return T[jj * sj + i]; };
     auto dy = [&](int jj) { return dya[jj * sj + i]; };
-    A[p] = fv3::ppm_flux_staged<MORD>(qy, ty, dy, cry[p], j, ey);
+    A[p] = fv3::ppm_flux_staged<MORD>(qy, ty, dy, v[0], j, ey);
   });
   // 3. cube-corner blocks as copy_corners_x leaves them
   b.par(4 * h * h, [&](int t) {
@@ -87,24 +88,32 @@ FV_DEV void fvtp2d_plane(const fv3_geom &g, const fv3_grid &m, int s, int k, con
     auto dx = [&](int ii) { return dxa[j * sj + ii]; };
     T[j * sj + i] = fv3::ppm_stage<MORD>(qx, dx, i, ex);
   });
-  b.par2(nx + 1, nwj, [&](int ir, int j) {
+  b.par2_pre<1>(nx + 1, nwj, [&](int ir, int j, double *v) { v[0] = FV_LDG(crx + j * sj + isc + ir); },
+                [&](int ir, int j, const double *v) {
     const int i = isc + ir, p = j * sj + i;
     auto qx = [&](int ii) { return Q[j * sj + ii]; };
     auto tx = [&](int ii) { return T[j * sj + ii]; };
     auto dx = [&](int ii) { return dxa[j * sj + ii]; };
-    B[p] = fv3::ppm_flux_staged<MORD>(qx, tx, dx, crx[p], i, ex);
+    B[p] = fv3::ppm_flux_staged<MORD>(qx, tx, dx, v[0], i, ex);
   });
   // 5. transverse updates: q_i (into Q, compute rows) and q_j (into D, compute columns)
-  b.par2(nwi, nwj, [&](int i, int j) {
+  b.par2_pre<5>(nwi, nwj, [&](int i, int j, double *v) {
     const int p = j * sj + i;
-    const double qv = Q[p], ar = area[p];
+    v[0] = FV_LDG(area + p);
+    v[1] = FV_LDG(yfx + p);
+    v[2] = FV_LDG(yfx + p + sj);
+    v[3] = FV_LDG(xfx + p);
+    v[4] = FV_LDG(xfx + p + 1);
+  }, [&](int i, int j, const double *v) {
+    const int p = j * sj + i;
+    const double qv = Q[p], ar = v[0];
     if (j >= jsc && j <= jec) {
-      const double f0 = yfx[p] * A[p], f1 = yfx[p + sj] * A[p + sj];
-      Q[p] = (qv * ar + f0 - f1) / (ar + yfx[p] - yfx[p + sj]);
+      const double f0 = v[1] * A[p], f1 = v[2] * A[p + sj];
+      Q[p] = (qv * ar + f0 - f1) / (ar + v[1] - v[2]);
     }
     if (i >= isc && i <= iec) {
-      const double f0 = xfx[p] * B[p], f1 = xfx[p + 1] * B[p + 1];
-      D[p] = (qv * ar + f0 - f1) / (ar + xfx[p] - xfx[p + 1]);
+      const double f0 = v[3] * B[p], f1 = v[4] * B[p + 1];
+      D[p] = (qv * ar + f0 - f1) / (ar + v[3] - v[4]);
     }
   });
   // 6. outer x sweep on q_i (compute rows) -> x flux, in place over fx_in
@@ -115,13 +124,17 @@ FV_DEV void fvtp2d_plane(const fv3_geom &g, const fv3_grid &m, int s, int k, con
     auto dx = [&](int ii) { return dxa[j * sj + ii]; };
     T[j * sj + i] = fv3::ppm_stage<MORD>(qx, dx, i, ex);
   });
-  b.par2(nx + 1, ny, [&](int ir, int jr) {
+  b.par2_pre<2>(nx + 1, ny, [&](int ir, int jr, double *v) {
+    const int p = (jsc + jr) * sj + isc + ir;
+    v[0] = FV_LDG(crx + p);
+    v[1] = FV_LDG(xu + p);
+  }, [&](int ir, int jr, const double *v) {
     const int i = isc + ir, j = jsc + jr, p = j * sj + i;
     auto qx = [&](int ii) { return Q[j * sj + ii]; };
     auto tx = [&](int ii) { return T[j * sj + ii]; };
     auto dx = [&](int ii) { return dxa[j * sj + ii]; };
-    const double outer = fv3::ppm_flux_staged<MORD>(qx, tx, dx, crx[p], i, ex);
-    B[p] = 0.5 * (outer + B[p]) * xu[p];
+    const double outer = fv3::ppm_flux_staged<MORD>(qx, tx, dx, v[0], i, ex);
+    B[p] = 0.5 * (outer + B[p]) * v[1];
   });
   // 7. outer y sweep on q_j (compute columns) -> y flux, in place over fy_in
   b.par2(nx, ny + stn, [&](int ir, int jr) {
@@ -130,13 +143,17 @@ FV_DEV void fvtp2d_plane(const fv3_geom &g, const fv3_grid &m, int s, int k, con
     auto dy = [&](int jj) { return dya[jj * sj + i]; };
     T[j * sj + i] = fv3::ppm_stage<MORD>(qy, dy, j, ey);
   });
-  b.par2(nx, ny + 1, [&](int ir, int jr) {
+  b.par2_pre<2>(nx, ny + 1, [&](int ir, int jr, double *v) {
+    const int p = (jsc + jr) * sj + isc + ir;
+    v[0] = FV_LDG(cry + p);
+    v[1] = FV_LDG(yu + p);
+  }, [&](int ir, int jr, const double *v) {
     const int i = isc + ir, j = jsc + jr, p = j * sj + i;
     auto qy = [&](int jj) { return D[jj * sj + i]; };
     auto ty = [&](int jj) { return T[jj * sj + i]; };
     auto dy = [&](int jj) { return dya[jj * sj + i]; };
-    const double outer = fv3::ppm_flux_staged<MORD>(qy, ty, dy, cry[p], j, ey);
-    A[p] = 0.5 * (outer + A[p]) * yu[p];
+    const double outer = fv3::ppm_flux_staged<MORD>(qy, ty, dy, v[0], j, ey);
+    A[p] = 0.5 * (outer + A[p]) * v[1];
   });
 }
 

@@ -29,6 +29,17 @@ struct Block {
     for (int jr = 0; jr < nrows; ++jr)
       for (int ir = 0; ir < w; ++ir) f(ir, jr);
   }
+  // as par2, with the global-memory operands of a point fetched by `load(ir, jr, v)` into NV registers before
+  // `comp(ir, jr, v)` runs
+  template <int NV, class L, class C>
+  void par2_pre(int w, int nrows, L load, C comp) const {
+    for (int jr = 0; jr < nrows; ++jr)
+      for (int ir = 0; ir < w; ++ir) {
+        double v[NV];
+        load(ir, jr, v);
+        comp(ir, jr, v);
+      }
+  }
 #else
   template <class F>
   __device__ __forceinline__ void par(int n, F f) const {
@@ -44,6 +55,46 @@ struct Block {
     for (int t = threadIdx.x; t < n; t += blockDim.x) {
       const int jr = (int)(((float)t + 0.5f) * inv);
       f(t - jr * w, jr);
+    }
+    __syncthreads();
+  }
+  // Software-pipelined form: each thread first issues the global loads of 2 or 4 of its points (independent
+  // LDG.NC requests in flight; out-of-range slots re-load the first point, results unused), then computes them.  With one CTA per SM (shared memory bound) this is what hides
+  // the L2 / HBM latency that the barrier-separated phases would otherwise expose.
+  template <int NV, class L, class C>
+  __device__ __forceinline__ void par2_pre(int w, int nrows, L load, C comp) const {
+    const int n = w * nrows, nt = blockDim.x;
+    const float inv = 1.0f / (float)w;
+    if (NV >= 4) {
+      for (int t0 = threadIdx.x; t0 < n; t0 += 2 * nt) {
+        const int t1 = t0 + nt;
+        const bool h1 = t1 < n;
+        const int j0 = (int)(((float)t0 + 0.5f) * inv), i0 = t0 - j0 * w;
+        const int j1 = h1 ? (int)(((float)t1 + 0.5f) * inv) : j0, i1 = h1 ? t1 - j1 * w : i0;
+        double v0[NV], v1[NV];
+        load(i0, j0, v0);
+        load(i1, j1, v1);
+        comp(i0, j0, v0);
+        if (h1) comp(i1, j1, v1);
+      }
+    } else {
+      for (int t0 = threadIdx.x; t0 < n; t0 += 4 * nt) {
+        const int t1 = t0 + nt, t2 = t1 + nt, t3 = t2 + nt;
+        const bool h1 = t1 < n, h2 = t2 < n, h3 = t3 < n;
+        const int j0 = (int)(((float)t0 + 0.5f) * inv), i0 = t0 - j0 * w;
+        const int j1 = h1 ? (int)(((float)t1 + 0.5f) * inv) : j0, i1 = h1 ? t1 - j1 * w : i0;
+        const int j2 = h2 ? (int)(((float)t2 + 0.5f) * inv) : j0, i2 = h2 ? t2 - j2 * w : i0;
+        const int j3 = h3 ? (int)(((float)t3 + 0.5f) * inv) : j0, i3 = h3 ? t3 - j3 * w : i0;
+        double v0[NV], v1[NV], v2[NV], v3[NV];
+        load(i0, j0, v0);
+        load(i1, j1, v1);
+        load(i2, j2, v2);
+        load(i3, j3, v3);
+        comp(i0, j0, v0);
+        if (h1) comp(i1, j1, v1);
+        if (h2) comp(i2, j2, v2);
+        if (h3) comp(i3, j3, v3);
+      }
     }
     __syncthreads();
   }
