@@ -8,6 +8,7 @@
 #include "common.h"
 #include "plane.h"
 #include "ppm.h"
+#include "sweep.h"
 
 namespace {
 
@@ -50,29 +51,14 @@ FV_DEV void fvtp2d_plane(const fv3_geom &g, const fv3_grid &m, int s, int k, con
   const fv3::Edge1D ex{fv3::on_west(g, s), fv3::on_east(g, s), isc, iec};
   const fv3::Edge1D ey{fv3::on_south(g, s), fv3::on_north(g, s), jsc, jec};
   const int nwi = ied + 1, nwj = jed + 1;
-  // staging ranges: al on faces start-1 .. end+2, dm on cells start-2 .. end+2
-  const int st0 = MORD < 8 ? -1 : -2, stn = MORD < 8 ? 4 : 5;
   // 1. load q; 3x3 cube-corner halo blocks as copy_corners_y leaves them
-  b.par2_pre<1>(nwi, nwj, [&](int i, int j, double *v) {
+  b.par2(nwi, nwj, [&](int i, int j) {
     int ii = i, jj = j;
-    fv3::corner_y(g, s, ii, jj);
-    v[0] = FV_LDG(q + jj * sj + ii);
-  }, [&](int i, int j, const double *v) { Q[j * sj + i] = v[0]; });
+    if ((i < isc || i > iec) && (j < jsc || j > jec)) fv3::corner_y(g, s, ii, jj);
+    Q[j * sj + i] = FV_LDG(q + jj * sj + ii);
+  });
   // 2. inner y sweep on q: all columns, faces jsc .. jec+1
-  b.par2(nwi, ny + stn, [&](int i, int jr) {
-    const int j = jsc + st0 + jr;
-    auto qy = [&](int jj) { return Q[jj * sj + i]; };
-    auto dy = [&](int jj) { return dya[jj * sj + i]; };
-    T[j * sj + i] = fv3::ppm_stage<MORD>(qy, dy, j, ey);
-  });
-  b.par2_pre<1>(nwi, ny + 1, [&](int i, int jr, double *v) { v[0] = FV_LDG(cry + (jsc + jr) * sj + i); },
-                [&](int i, int jr, const double *v) {
-    const int j = jsc + jr, p = j * sj + i;
-    auto qy = [&](int jj) { return Q[jj * sj + i]; };
-    auto ty = [&](int jj) { return T[jj * sj + i]; };
-    auto dy = [&](int jj) { return dya[jj * sj + i]; };
-    A[p] = fv3::ppm_flux_staged<MORD>(qy, ty, dy, v[0], j, ey);
-  });
+  fv3::ppm_sweep<MORD, false>(b, Q, T, sj, cry, dya, ey, 0, nwi, [&](int p, double val) { A[p] = val; });
   // 3. cube-corner blocks as copy_corners_x leaves them
   b.par(4 * h * h, [&](int t) {
     const int c = t / (h * h), r = t - c * h * h, a1 = r / h, b1 = r - a1 * h;
@@ -82,79 +68,29 @@ FV_DEV void fvtp2d_plane(const fv3_geom &g, const fv3_grid &m, int s, int k, con
     Q[j * sj + i] = q[jj * sj + ii];
   });
   // 4. inner x sweep on q: all rows, faces isc .. iec+1
-  b.par2(nx + stn, nwj, [&](int ir, int j) {
-    const int i = isc + st0 + ir;
-    auto qx = [&](int ii) { return Q[j * sj + ii]; };
-    auto dx = [&](int ii) { return dxa[j * sj + ii]; };
-    T[j * sj + i] = fv3::ppm_stage<MORD>(qx, dx, i, ex);
-  });
-  b.par2_pre<1>(nx + 1, nwj, [&](int ir, int j, double *v) { v[0] = FV_LDG(crx + j * sj + isc + ir); },
-                [&](int ir, int j, const double *v) {
-    const int i = isc + ir, p = j * sj + i;
-    auto qx = [&](int ii) { return Q[j * sj + ii]; };
-    auto tx = [&](int ii) { return T[j * sj + ii]; };
-    auto dx = [&](int ii) { return dxa[j * sj + ii]; };
-    B[p] = fv3::ppm_flux_staged<MORD>(qx, tx, dx, v[0], i, ex);
-  });
+  fv3::ppm_sweep<MORD, true>(b, Q, T, sj, crx, dxa, ex, 0, nwj, [&](int p, double val) { B[p] = val; });
   // 5. transverse updates: q_i (into Q, compute rows) and q_j (into D, compute columns)
-  b.par2_pre<5>(nwi, nwj, [&](int i, int j, double *v) {
+  b.par2(nwi, nwj, [&](int i, int j) {
     const int p = j * sj + i;
-    v[0] = FV_LDG(area + p);
-    v[1] = FV_LDG(yfx + p);
-    v[2] = FV_LDG(yfx + p + sj);
-    v[3] = FV_LDG(xfx + p);
-    v[4] = FV_LDG(xfx + p + 1);
-  }, [&](int i, int j, const double *v) {
-    const int p = j * sj + i;
-    const double qv = Q[p], ar = v[0];
+    const double qv = Q[p], ar = FV_LDG(area + p);
     if (j >= jsc && j <= jec) {
-      const double f0 = v[1] * A[p], f1 = v[2] * A[p + sj];
-      Q[p] = (qv * ar + f0 - f1) / (ar + v[1] - v[2]);
+      const double y0 = FV_LDG(yfx + p), y1 = FV_LDG(yfx + p + sj);
+      const double f0 = y0 * A[p], f1 = y1 * A[p + sj];
+      Q[p] = (qv * ar + f0 - f1) / (ar + y0 - y1);
     }
     if (i >= isc && i <= iec) {
-      const double f0 = v[3] * B[p], f1 = v[4] * B[p + 1];
-      D[p] = (qv * ar + f0 - f1) / (ar + v[3] - v[4]);
+      const double x0 = FV_LDG(xfx + p), x1 = FV_LDG(xfx + p + 1);
+      const double f0 = x0 * B[p], f1 = x1 * B[p + 1];
+      D[p] = (qv * ar + f0 - f1) / (ar + x0 - x1);
     }
   });
   // 6. outer x sweep on q_i (compute rows) -> x flux, in place over fx_in
   const double *xu = a.xu + ob, *yu = a.yu + ob;
-  b.par2(nx + stn, ny, [&](int ir, int jr) {
-    const int i = isc + st0 + ir, j = jsc + jr;
-    auto qx = [&](int ii) { return Q[j * sj + ii]; };
-    auto dx = [&](int ii) { return dxa[j * sj + ii]; };
-    T[j * sj + i] = fv3::ppm_stage<MORD>(qx, dx, i, ex);
-  });
-  b.par2_pre<2>(nx + 1, ny, [&](int ir, int jr, double *v) {
-    const int p = (jsc + jr) * sj + isc + ir;
-    v[0] = FV_LDG(crx + p);
-    v[1] = FV_LDG(xu + p);
-  }, [&](int ir, int jr, const double *v) {
-    const int i = isc + ir, j = jsc + jr, p = j * sj + i;
-    auto qx = [&](int ii) { return Q[j * sj + ii]; };
-    auto tx = [&](int ii) { return T[j * sj + ii]; };
-    auto dx = [&](int ii) { return dxa[j * sj + ii]; };
-    const double outer = fv3::ppm_flux_staged<MORD>(qx, tx, dx, v[0], i, ex);
-    B[p] = 0.5 * (outer + B[p]) * v[1];
-  });
+  fv3::ppm_sweep<MORD, true>(b, Q, T, sj, crx, dxa, ex, jsc, ny,
+                             [&](int p, double val) { B[p] = 0.5 * (val + B[p]) * FV_LDG(xu + p); });
   // 7. outer y sweep on q_j (compute columns) -> y flux, in place over fy_in
-  b.par2(nx, ny + stn, [&](int ir, int jr) {
-    const int i = isc + ir, j = jsc + st0 + jr;
-    auto qy = [&](int jj) { return D[jj * sj + i]; };
-    auto dy = [&](int jj) { return dya[jj * sj + i]; };
-    T[j * sj + i] = fv3::ppm_stage<MORD>(qy, dy, j, ey);
-  });
-  b.par2_pre<2>(nx, ny + 1, [&](int ir, int jr, double *v) {
-    const int p = (jsc + jr) * sj + isc + ir;
-    v[0] = FV_LDG(cry + p);
-    v[1] = FV_LDG(yu + p);
-  }, [&](int ir, int jr, const double *v) {
-    const int i = isc + ir, j = jsc + jr, p = j * sj + i;
-    auto qy = [&](int jj) { return D[jj * sj + i]; };
-    auto ty = [&](int jj) { return T[jj * sj + i]; };
-    auto dy = [&](int jj) { return dya[jj * sj + i]; };
-    const double outer = fv3::ppm_flux_staged<MORD>(qy, ty, dy, v[0], j, ey);
-    A[p] = 0.5 * (outer + A[p]) * v[1];
-  });
+  fv3::ppm_sweep<MORD, false>(b, D, T, sj, cry, dya, ey, isc, nx,
+                              [&](int p, double val) { A[p] = 0.5 * (val + A[p]) * FV_LDG(yu + p); });
 }
 
 // ---- plane-resident del-n fluxes (DelnFlux / DelnFluxNoSG, delnflux.py:59-238,1164-1261) ------------------------
