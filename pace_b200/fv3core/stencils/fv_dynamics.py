@@ -87,6 +87,30 @@ class DynamicalCore:
 
     __call__ = step_dynamics
 
+    def capture_step(self, state: DycoreState, warmup: int = 1):
+        """Capture one `step_dynamics(state)` — every kernel launch and halo exchange of the timestep — into a CUDA
+        graph and return `replay()`, which advances `state` in place by one timestep per call.
+
+        B200-first replacement of the reference's DaCe orchestration (dsl/pace/dsl/dace/orchestration.py): the step is
+        ~1600 short launches, so on a GPU that owns only a few subdomains the host enqueue time would otherwise bound
+        the step.  The stage sequence is static (n_split, k_split fixed at construction), which is what makes it
+        capturable.  The checkpointer must be off."""
+        if self.call_checkpointer:
+            raise RuntimeError("capture_step cannot be used with a checkpointer")
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.step_dynamics(state)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.step_dynamics(state)
+        self._graph = graph
+        return graph.replay
+
     def compute_preamble(self, state, is_root_rank: bool = True):
         self._rt.call("fv3_fv_setup", self._t6.data_ptr(), state.q_con.ptr, self._cvm.ptr, state.pkz.ptr, state.pt.ptr,
                       self._cappa.ptr, state.delp.ptr, state.delz.ptr, self._dp_initial.ptr)
