@@ -202,6 +202,11 @@ int fv3_remap_prep(fv3_ctx *ctx, double *const *tracers6, double *q_con, double 
  * (qs_is_2d = 1) or a 3-D field read at level 0; i_extra / j_extra = 1 for x- / y-interface fields (v / u). */
 int fv3_map_single(fv3_ctx *ctx, double *q1, const double *pe1, const double *pe2, const double *qs, int qs_is_2d,
                    double qmin, int kord, int iv, int i_extra, int j_extra, void *stream);
+/* n (<= 16) independent MapSingle calls in ONE launch (MapNTracer.__call__, mapn_tracer.py:60-82, and the
+ * per-field calls of remapping.py:560-640).  desc: HOST array of n records of 8 int64 {q1, pe1, pe2, qs (0 = none),
+ * qs_is_2d, iv, i_extra, j_extra} (device addresses as integers); qmin: HOST array of n doubles.  Both are consumed
+ * before the call returns. */
+int fv3_map_multi(fv3_ctx *ctx, int n, const int64_t *desc, const double *qmin, int kord, void *stream);
 /* FillNegativeTracerValues.__call__ (fillz.py:15-163) for nq tracers (device array of nq pointers) */
 int fv3_fillz(fv3_ctx *ctx, double *const *tracers, int nq, const double *dp2, void *stream);
 int fv3_remap_post(fv3_ctx *ctx, double *const *tracers6, double *q_con, double *pkz, const double *pt, double *cappa,

@@ -51,6 +51,15 @@ FV_DEV void fvtp2d_plane(const fv3_geom &g, const fv3_grid &m, int s, int k, con
   const fv3::Edge1D ex{fv3::on_west(g, s), fv3::on_east(g, s), isc, iec};
   const fv3::Edge1D ey{fv3::on_south(g, s), fv3::on_north(g, s), jsc, jec};
   const int nwi = ied + 1, nwj = jed + 1;
+  {  // operands of the later phases: start their HBM -> L2 transfer now
+    const int pl = g.nj * sj;
+    b.prefetch_l2(cry, pl);
+    b.prefetch_l2(crx, pl);
+    b.prefetch_l2(yfx, pl);
+    b.prefetch_l2(xfx, pl);
+    if (a.xu != a.xfx) b.prefetch_l2(a.xu + ob, pl);
+    if (a.yu != a.yfx) b.prefetch_l2(a.yu + ob, pl);
+  }
   // 1. load q; 3x3 cube-corner halo blocks as copy_corners_y leaves them
   b.par2(nwi, nwj, [&](int i, int j) {
     int ii = i, jj = j;
@@ -153,9 +162,10 @@ int fvtp2d_launch(const fv3_ctx *ctx, cudaStream_t st, PlaneArgs a, double *fx, 
   const int PL = g.nj * g.sj;
   return fv3::launch_planes(ctx, st, 0, nk, FVTP_PLANES * PL, FV_LAMBDA(int s, int k, const fv3::Block &b) { FV_DEV_GM
     double *Q = b.sm, *A = Q + PL, *B = A + PL, *D = B + PL, *T = D + PL;
+    const int64_t ob = O3(s, 0, 0, k);
+    if (mode == 2) b.prefetch_l2(mass + ob, PL);
     fvtp2d_plane<MORD>(g, m, s, k, b, a, Q, A, B, D, T);
     const int sj = g.sj, h = g.halo, nx = g.nx, ny = g.ny;
-    const int64_t ob = O3(s, 0, 0, k);
     if (mode == 0) {
       b.par2(nx + 1, ny + 1, [&](int ir, int jr) {
         const int p = (h + jr) * sj + h + ir;
@@ -262,8 +272,10 @@ int fv3_tracer_subcycle(fv3_ctx *ctx, double *const *tracers, int nq, double *dp
     const int sj = g.sj, h = g.halo, nx = g.nx;
     const int64_t ob = O3(s, 0, 0, k), o2b = O2(s, 0, 0);
     const double *rarea = m.rarea + o2b;
+    b.prefetch_l2(dp1 + ob, PL);
     for (int n = 0; n < nq; ++n) {
       double *q = tracers[n];
+      if (n + 1 < nq) b.prefetch_l2(tracers[n + 1] + ob, PL);
       const PlaneArgs pa{q, cx, cy, xfx, yfx, mfx, mfy};
       fvtp2d_plane<8>(g, m, s, k, b, pa, Q, A, B, D, T);
       b.par(nx * g.ny, [&](int t) {

@@ -39,6 +39,11 @@ int fv3_nh_p_grad(fv3_ctx *ctx, double *u, double *v, double *pp, double *gz, do
         dst[ob + p] = value;
       });
     };
+    if (k >= 1) {
+      b.prefetch_l2(pp + ob, PL);
+      b.prefetch_l2(pk3 + ob, PL);
+    }
+    if (k < nz) b.prefetch_l2(delp + ob, PL);
     fv3::a2b_plane(g, m, s, b, gz + ob, SQ, QX, QY, OUT);
     store(gzb);
     if (k >= 1) {

@@ -19,6 +19,7 @@ constexpr int PLANE_THREADS = 1024;
 struct Block {
   double *sm;
 #ifdef FV3_HOSTSIM
+  void prefetch_l2(const double *, int) const {}
   template <class F>
   void par(int n, F f) const {
     for (int t = 0; t < n; ++t) f(t);
@@ -41,6 +42,12 @@ struct Block {
       }
   }
 #else
+  // One bulk L2 prefetch (cp.async.bulk.prefetch.L2) of n contiguous doubles — a whole (s, k) plane of a field is
+  // contiguous in HBM — issued by one thread: operands of later phases are pulled into L2 while the CTA computes.
+  __device__ __forceinline__ void prefetch_l2(const double *p, int n) const {
+    if (threadIdx.x == 0)
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"((n * 8) & ~15) : "memory");
+  }
   template <class F>
   __device__ __forceinline__ void par(int n, F f) const {
     for (int t = threadIdx.x; t < n; t += blockDim.x) f(t);

@@ -1,7 +1,9 @@
-// Lagrangian-to-Eulerian vertical remapping: one thread per column, profiles in thread-local arrays.
+// Lagrangian-to-Eulerian vertical remapping.
 //   fv3_remap_prep      <- init_pe + moist_cv_pt_pressure + pn2_pk_delp (remapping.py:34-193)
-//   fv3_map_single      <- MapSingle.__call__ (map_single.py:147-200): RemapProfile (remap_profile.py:150-563,
-//                          kord 9) + lagrangian_contributions (map_single.py:21-81)
+//   fv3_map_multi       <- n independent MapSingle.__call__ (map_single.py:147-200) in one launch: RemapProfile
+//                          (remap_profile.py:150-563, kord 9) + lagrangian_contributions (map_single.py:21-81);
+//                          MapNTracer (mapn_tracer.py:60-82) is the same call over the tracers
+//   fv3_map_single      <- one MapSingle.__call__ (a batch of one)
 //   fv3_fillz           <- FillNegativeTracerValues.__call__ (fillz.py:15-163)
 //   fv3_remap_post      <- undo_delz_adjust_and_copy_peln + moist_pkz (remapping.py:46-59, moist_cv.py:112-141)
 //   fv3_remap_pressures <- pressures_mapu / pressures_mapv (remapping.py:196-254)
@@ -16,10 +18,6 @@ constexpr int NKMAX = 96;
 constexpr double RDGAS = 287.05, GRAV = 9.80665, CP_AIR = 1004.6, RVGAS = 461.50;
 constexpr double RDG = -RDGAS / GRAV, CV_AIR = CP_AIR - RDGAS, CV_VAP = 3.0 * RVGAS, C_LIQ = 4.1855e3, C_ICE = 1972.0;
 constexpr double ZVIR = RVGAS / RDGAS - 1;
-
-struct Profile {
-  double a1[NKMAX], a2[NKMAX], a3[NKMAX], a4[NKMAX];
-};
 
 FV_HD void posdef_iv1(double &a1, double &a2, double &a3, double &a4) {
   const double da1 = a3 - a2, da2 = da1 * da1, a6da = a4 * da1;
@@ -71,170 +69,345 @@ FV_HD void posdef_iv0(double &a1, double &a2, double &a3, double &a4) {
 FV_HD double min3(double a, double b, double c) { return (a < b && a < c) ? a : (b < c ? b : c); }
 FV_HD double max3(double a, double b, double c) { return (a > b && a > c) ? a : (b > c ? b : c); }
 
-// RemapProfile.__call__ for kord == 9 (remap_profile.py:622-681).  p.a1 holds the layer means on entry.
-FV_HD void remap_profile(Profile &p, const double *delp, int km, int iv, double qs, double qmin) {
-  double q[NKMAX], gam[NKMAX];
-  bool extm[NKMAX];
-  const double *a1 = p.a1;
-  // set_initial_vals (:150-250)
-  if (iv != -2) {
-    {
-      const double gr = delp[1] / delp[0], bet = gr * (gr + 0.5);
-      q[0] = ((gr + gr) * (gr + 1.0) * a1[0] + a1[1]) / bet;
-      gam[0] = (1.0 + gr * (gr + 1.5)) / bet;
-    }
-    for (int k = 1; k < km; ++k) {
-      const double d4 = delp[k - 1] / delp[k], bet = 2.0 + d4 + d4 - gam[k - 1];
-      q[k] = (3.0 * (a1[k - 1] + d4 * a1[k]) - q[k - 1]) / bet;
-      gam[k] = d4 / bet;
-    }
-    {
-      const double d4 = delp[km - 2] / delp[km - 1], a_bot = 1.0 + d4 * (d4 + 1.5);
-      q[km] = (2.0 * d4 * (d4 + 1.0) * a1[km - 1] + a1[km - 2] - a_bot * q[km - 1]) / (d4 * (d4 + 0.5) - a_bot * gam[km - 1]);
-    }
-    for (int k = km - 1; k >= 0; --k) q[k] = q[k] - gam[k] * q[k + 1];
-  } else {
-    double gr[NKMAX];
-    q[0] = 1.5 * a1[0];
-    gam[1] = 0.5;
-    gr[1] = delp[0] / delp[1];
-    q[1] = (3.0 * (a1[0] + a1[1]) - q[0]) / (2.0 + gr[1] + gr[1] - gam[1]);
-    for (int k = 2; k < km; ++k) {
-      const double old_gr = delp[k - 2] / delp[k - 1], old_bet = 2.0 + old_gr + old_gr - gam[k - 1];
-      gam[k] = old_gr / old_bet;
-      gr[k] = delp[k - 1] / delp[k];
-    }
-    for (int k = 2; k < km - 1; ++k) {
-      const double bet = 2.0 + gr[k] + gr[k] - gam[k];
-      q[k] = (3.0 * (a1[k - 1] + a1[k]) - q[k - 1]) / bet;
-    }
-    q[km - 1] = (3.0 * (a1[km - 2] + a1[km - 1]) - gr[km - 1] * qs - q[km - 2]) / (2.0 + gr[km - 1] + gr[km - 1] - gam[km - 1]);
-    q[km] = qs;
-    for (int k = km - 2; k >= 0; --k) q[k] = q[k] - gam[k + 1] * q[k + 1];
-  }
-  // apply_constraints (:253-337)
-  for (int k = 1; k < km; ++k) gam[k] = a1[k] - a1[k - 1];
-  for (int k = 1; k < km; ++k) {
-    const double tmp = a1[k - 1] > a1[k] ? a1[k - 1] : a1[k], tmp2 = a1[k - 1] < a1[k] ? a1[k - 1] : a1[k];
-    if (k == 1 || k == km - 1) {
-      if (q[k] >= tmp) q[k] = tmp;
-      if (q[k] <= tmp2) q[k] = tmp2;
-    } else if (gam[k - 1] * gam[k + 1] > 0) {
-      if (q[k] >= tmp) q[k] = tmp;
-      if (q[k] <= tmp2) q[k] = tmp2;
-    } else if (gam[k - 1] > 0) {
-      if (q[k] <= tmp2) q[k] = tmp2;
-    } else {
-      if (q[k] >= tmp) q[k] = tmp;
-      if (iv == 0 && q[k] < 0.0) q[k] = 0.0;
-    }
-  }
-  for (int k = 0; k < km; ++k) {
-    p.a2[k] = q[k];
-    p.a3[k] = q[k + 1];
-  }
-  extm[0] = (p.a2[0] - a1[0]) * (p.a3[0] - a1[0]) > 0.0;
-  for (int k = 1; k < km - 1; ++k) extm[k] = gam[k] * gam[k + 1] < 0.0;
-  extm[km - 1] = (p.a2[km - 1] - a1[km - 1]) * (p.a3[km - 1] - a1[km - 1]) > 0.0;
-  // set_interpolation_coefficients (:340-563)
-  if (iv == 0 && p.a2[0] < 0.0) p.a2[0] = 0.0;
-  if (iv == -1 && p.a2[0] * a1[0] <= 0.0) p.a2[0] = 0.0;
-  for (int k = 0; k < 2; ++k) p.a4[k] = 3.0 * (2.0 * a1[k] - (p.a2[k] + p.a3[k]));
-  posdef_iv1(p.a1[0], p.a2[0], p.a3[0], p.a4[0]);
-  remap_constraint(p.a1[1], p.a2[1], p.a3[1], p.a4[1], extm[1]);
-  for (int k = 2; k < km - 2; ++k) {
-    const double v1 = a1[k];
-    const double pmp_1 = v1 - 2.0 * gam[k + 1], lac_1 = pmp_1 + 1.5 * gam[k + 2];
-    const double pmp_2 = v1 + 2.0 * gam[k], lac_2 = pmp_2 - 1.5 * gam[k - 1];
-    if ((extm[k] && extm[k - 1]) || (extm[k] && extm[k + 1]) || (extm[k] && (qmin > 0.0 && v1 < qmin))) {
-      p.a2[k] = v1;
-      p.a3[k] = v1;
-      p.a4[k] = 0.0;
-    } else {
-      p.a4[k] = 6.0 * v1 - 3.0 * (p.a2[k] + p.a3[k]);
-      if (fabs(p.a4[k]) > fabs(p.a2[k] - p.a3[k])) {
-        double tmin = min3(v1, pmp_1, lac_1), tmax = max3(v1, pmp_1, lac_1);
-        double t0 = p.a2[k] > tmin ? p.a2[k] : tmin;
-        p.a2[k] = t0 < tmax ? t0 : tmax;
-        tmin = min3(v1, pmp_2, lac_2);
-        tmax = max3(v1, pmp_2, lac_2);
-        t0 = p.a3[k] > tmin ? p.a3[k] : tmin;
-        p.a3[k] = t0 < tmax ? t0 : tmax;
-        p.a4[k] = 6.0 * v1 - 3.0 * (p.a2[k] + p.a3[k]);
-      }
-    }
-    if (iv == 0) posdef_iv0(p.a1[k], p.a2[k], p.a3[k], p.a4[k]);
-  }
-  if (iv == 0 && p.a3[km - 1] < 0.0) p.a3[km - 1] = 0.0;
-  if (iv == -1 && p.a3[km - 1] * a1[km - 1] <= 0.0) p.a3[km - 1] = 0.0;
-  for (int k = km - 2; k < km; ++k) p.a4[k] = 3.0 * (2.0 * a1[k] - (p.a2[k] + p.a3[k]));
-  remap_constraint(p.a1[km - 2], p.a2[km - 2], p.a3[km - 2], p.a4[km - 2], extm[km - 2]);
-  posdef_iv1(p.a1[km - 1], p.a2[km - 1], p.a3[km - 1], p.a4[km - 1]);
-}
-
 FV_HD void moist_cv(double qv, double ql_, double qr, double qs_, double qi, double qg, double &cvm, double &gz) {
   const double ql = ql_ + qr, qs = qi + qs_ + qg;
   gz = ql + qs;
   cvm = (1.0 - (qv + gz)) * CV_AIR + qv * CV_VAP + ql * C_LIQ + qs * C_ICE;
 }
 
+// ---- MapSingle as independent "chains" (one column of one field) -----------------------------------------------------
+// A chain keeps ONE array in fast storage: the interface values q[0..km] (shared memory, [level][lane]); the
+// tridiagonal factors gam[k] and later the remapped column go through a private column of a scratch field (G); the
+// layer means a1 and the pressures are re-read from the (L2-resident) inputs, and the PPM coefficients of a source
+// layer are rebuilt from q and a1 when the Lagrangian walk enters it.  All fields of a remap call go in one launch.
+// Expressions and their order follow the reference statement by statement (RemapProfile.__call__ for kord 9,
+// remap_profile.py:622-681).
+constexpr int MAP_MAX = 16;
+constexpr int MAP_NT = 32;
+struct MapBatch {
+  int n;
+  double *q1[MAP_MAX];
+  const double *pe1[MAP_MAX], *pe2[MAP_MAX], *qs[MAP_MAX];
+  double *out[MAP_MAX];
+  double qmin[MAP_MAX];
+  int qs2d[MAP_MAX], iv[MAP_MAX], iex[MAP_MAX], jex[MAP_MAX];
+};
+
+// set_interpolation_coefficients (remap_profile.py:340-563) of source layer L from its interface values (b2, b3 on
+// entry) and the layer means a1[L-2 .. L+2] = (am2, am1, v1, ap1, ap2)
+FV_HD void map_coef(int L, int km, int iv, double qmin, double am2, double am1, double v1, double ap1, double ap2,
+                    double &b1, double &b2, double &b3, double &b4) {
+  b1 = v1;
+  if (L == 0) {
+    if (iv == 0 && b2 < 0.0) b2 = 0.0;
+    if (iv == -1 && b2 * v1 <= 0.0) b2 = 0.0;
+    b4 = 3.0 * (2.0 * v1 - (b2 + b3));
+    posdef_iv1(b1, b2, b3, b4);
+    return;
+  }
+  if (L == km - 1) {
+    if (iv == 0 && b3 < 0.0) b3 = 0.0;
+    if (iv == -1 && b3 * v1 <= 0.0) b3 = 0.0;
+    b4 = 3.0 * (2.0 * v1 - (b2 + b3));
+    posdef_iv1(b1, b2, b3, b4);
+    return;
+  }
+  const double g0 = v1 - am1, g1 = ap1 - v1;  // gam[L], gam[L+1] (differences of the layer means)
+  const bool ext0 = g0 * g1 < 0.0;
+  if (L == 1 || L == km - 2) {
+    b4 = 3.0 * (2.0 * v1 - (b2 + b3));
+    remap_constraint(b1, b2, b3, b4, ext0);
+    return;
+  }
+  const double gm1 = am1 - am2, g2 = ap2 - ap1;  // gam[L-1], gam[L+2]
+  const bool extm = gm1 * g0 < 0.0, extp = g1 * g2 < 0.0;
+  const double pmp_1 = v1 - 2.0 * g1, lac_1 = pmp_1 + 1.5 * g2;
+  const double pmp_2 = v1 + 2.0 * g0, lac_2 = pmp_2 - 1.5 * gm1;
+  if ((ext0 && extm) || (ext0 && extp) || (ext0 && (qmin > 0.0 && v1 < qmin))) {
+    b2 = v1;
+    b3 = v1;
+    b4 = 0.0;
+  } else {
+    b4 = 6.0 * v1 - 3.0 * (b2 + b3);
+    if (fabs(b4) > fabs(b2 - b3)) {
+      double tmin = min3(v1, pmp_1, lac_1), tmax = max3(v1, pmp_1, lac_1);
+      double t0 = b2 > tmin ? b2 : tmin;
+      b2 = t0 < tmax ? t0 : tmax;
+      tmin = min3(v1, pmp_2, lac_2);
+      tmax = max3(v1, pmp_2, lac_2);
+      t0 = b3 > tmin ? b3 : tmin;
+      b3 = t0 < tmax ? t0 : tmax;
+      b4 = 6.0 * v1 - 3.0 * (b2 + b3);
+    }
+  }
+  if (iv == 0) posdef_iv0(b1, b2, b3, b4);
+}
+
+// Inputs are read through the read-only path (FV_LDG) and streamed a few levels ahead of their use: q1 is only
+// written by this chain's final copy, after its last read.
+template <class QS, class GS>
+FV_DEV void map_chain(const fv3_geom &g, const MapBatch &mb, int f, int s, int i, int j, int km, QS Q, GS G) {
+  const int64_t c0 = O3(s, i, j, 0), sk = g.sk;
+  double *q1 = mb.q1[f];
+  const double *pe1 = mb.pe1[f] + c0, *pe2 = mb.pe2[f] + c0;
+  const double *a1p = q1 + c0;
+  const int iv = mb.iv[f];
+  const double qmin = mb.qmin[f];
+  auto A1 = [&](int k) { return FV_LDG(a1p + k * sk); };
+  auto P1 = [&](int k) { return FV_LDG(pe1 + k * sk); };
+  // set_initial_vals (remap_profile.py:150-250)
+  if (iv != -2) {
+    double p_k = P1(1), p_k1 = P1(2);
+    double dpm = p_k - P1(0), dpk = p_k1 - p_k;
+    double am = A1(0), ak = A1(1);
+    double qm, gm;
+    {
+      const double gr = dpk / dpm, bet = gr * (gr + 0.5);
+      qm = ((gr + gr) * (gr + 1.0) * am + ak) / bet;
+      gm = (1.0 + gr * (gr + 1.5)) / bet;
+      Q(0) = qm;
+      G(0) = gm;
+    }
+    double d4 = 0.0;
+#pragma unroll 4
+    for (int k = 1; k < km; ++k) {
+      d4 = dpm / dpk;
+      const double bet = 2.0 + d4 + d4 - gm;
+      qm = (3.0 * (am + d4 * ak) - qm) / bet;
+      gm = d4 / bet;
+      Q(k) = qm;
+      G(k) = gm;
+      if (k + 1 < km) {
+        dpm = dpk;
+        am = ak;
+        p_k = p_k1;
+        p_k1 = P1(k + 2);
+        dpk = p_k1 - p_k;
+        ak = A1(k + 1);
+      }
+    }
+    {
+      // d4 = delp[km-2] / delp[km-1], ak = a1[km-1], am = a1[km-2], qm = q[km-1], gm = gam[km-1]
+      const double a_bot = 1.0 + d4 * (d4 + 1.5);
+      Q(km) = (2.0 * d4 * (d4 + 1.0) * ak + am - a_bot * qm) / (d4 * (d4 + 0.5) - a_bot * gm);
+    }
+    double qn = Q(km);
+#pragma unroll 4
+    for (int k = km - 1; k >= 0; --k) {
+      qn = Q(k) - G(k) * qn;
+      Q(k) = qn;
+    }
+  } else {
+    double qsv = 0.0;
+    if (mb.qs[f] != nullptr) qsv = mb.qs2d[f] ? mb.qs[f][O2(s, i, j)] : mb.qs[f][c0];
+    double p_k = P1(1), p_k1 = P1(2);
+    double dpm = p_k - P1(0), dpk = p_k1 - p_k;  // delp[0], delp[1]
+    double am = A1(0), ak = A1(1);
+    const double q0 = 1.5 * am;
+    Q(0) = q0;
+    double gm = 0.5;  // gam[1]
+    G(1) = gm;
+    double grm = dpm / dpk;  // gr[1]
+    double qm = (3.0 * (am + ak) - q0) / (2.0 + grm + grm - gm);
+    Q(1) = qm;
+#pragma unroll 4
+    for (int k = 2; k < km; ++k) {
+      dpm = dpk;
+      am = ak;
+      p_k = p_k1;
+      p_k1 = P1(k + 1);
+      dpk = p_k1 - p_k;  // delp[k]
+      ak = A1(k);
+      const double old_bet = 2.0 + grm + grm - gm;
+      gm = grm / old_bet;  // gam[k]
+      G(k) = gm;
+      const double grk = dpm / dpk;  // gr[k]
+      if (k < km - 1) {
+        const double bet = 2.0 + grk + grk - gm;
+        qm = (3.0 * (am + ak) - qm) / bet;
+        Q(k) = qm;
+      } else {
+        Q(km - 1) = (3.0 * (am + ak) - grk * qsv - qm) / (2.0 + grk + grk - gm);
+      }
+      grm = grk;
+    }
+    Q(km) = qsv;
+    double qn = Q(km - 1);
+#pragma unroll 4
+    for (int k = km - 2; k >= 0; --k) {
+      qn = Q(k) - G(k + 1) * qn;
+      Q(k) = qn;
+    }
+  }
+  // apply_constraints (:253-337) on the interior interfaces
+  {
+    double a_m2 = 0.0, a_m1 = A1(0), a_0 = A1(1);
+#pragma unroll 4
+    for (int k = 1; k < km; ++k) {
+      const double a_p1 = k + 1 < km ? A1(k + 1) : 0.0;
+      const double tmp = a_m1 > a_0 ? a_m1 : a_0, tmp2 = a_m1 < a_0 ? a_m1 : a_0;
+      double qk = Q(k);
+      if (k == 1 || k == km - 1) {
+        if (qk >= tmp) qk = tmp;
+        if (qk <= tmp2) qk = tmp2;
+      } else {
+        const double g_m1 = a_m1 - a_m2, g_p1 = a_p1 - a_0;
+        if (g_m1 * g_p1 > 0) {
+          if (qk >= tmp) qk = tmp;
+          if (qk <= tmp2) qk = tmp2;
+        } else if (g_m1 > 0) {
+          if (qk <= tmp2) qk = tmp2;
+        } else {
+          if (qk >= tmp) qk = tmp;
+          if (iv == 0 && qk < 0.0) qk = 0.0;
+        }
+      }
+      Q(k) = qk;
+      a_m2 = a_m1;
+      a_m1 = a_0;
+      a_0 = a_p1;
+    }
+  }
+  // lagrangian_contributions (map_single.py:21-81).  L = absolute source layer.  Sliding register windows around
+  // it: layer means w[n] = a1[L-2+n] (n = 0..7) and pressures p[n] = pe1[L+n] (n = 0..4); the element entering a
+  // window is requested three layers before the coefficients of its layer are built.
+  int L = 0;
+  double w0 = 0.0, w1 = 0.0, w2 = A1(0), w3 = A1(1), w4 = A1(2), w5 = A1(3), w6 = A1(4), w7 = A1(5);
+  double p0 = P1(0), p1 = P1(1), p2 = P1(2), p3 = P1(3), p4 = P1(4);
+  auto shift = [&]() {  // L -> L + 1
+    w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; w5 = w6; w6 = w7;
+    w7 = L + 6 < km ? A1(L + 6) : 0.0;
+    p0 = p1; p1 = p2; p2 = p3; p3 = p4;
+    p4 = L + 5 <= km ? P1(L + 5) : 0.0;
+    L = L + 1;
+  };
+  double b1, b2 = Q(0), b3 = Q(1), b4;
+  map_coef(0, km, iv, qmin, w0, w1, w2, w3, w4, b1, b2, b3, b4);
+  double top = FV_LDG(pe2);
+  double bot_next = FV_LDG(pe2 + sk);
+  for (int k = 0; k < km; ++k) {
+    const double bot = bot_next;
+    if (k + 2 <= km) bot_next = FV_LDG(pe2 + (k + 2) * sk);
+    const double dpL = p1 - p0;
+    const double pl = (top - p0) / dpL;
+    double out;
+    if (bot <= p1) {
+      const double pr = (bot - p0) / dpL;
+      out = b2 + 0.5 * (b4 + b3 - b2) * (pr + pl) - b4 * 1.0 / 3.0 * (pr * (pr + pl) + pl * pl);
+    } else {
+      double qsum = (p1 - top) * (b2 + 0.5 * (b4 + b3 - b2) * (1.0 + pl) - b4 * 1.0 / 3.0 * (1.0 + pl * (1.0 + pl)));
+      // L = L + 1; while (L + 1 <= km and pe1[L+1] < bot): qsum += dp1[L] * a1[L]; L += 1; then L = min(L, km-1)
+      bool more = L < km - 1;
+      if (more) shift();
+      while (more && p1 < bot) {
+        qsum += (p1 - p0) * w2;
+        more = L < km - 1;
+        if (more) shift();
+      }
+      b2 = Q(L);
+      b3 = Q(L + 1);
+      map_coef(L, km, iv, qmin, w0, w1, w2, w3, w4, b1, b2, b3, b4);
+      const double dpn = p1 - p0;
+      const double dp = bot - p0, esl = dp / dpn;
+      qsum += dp * (b2 + 0.5 * esl * (b3 - b2 + b4 * (1.0 - (2.0 / 3.0) * esl)));
+      out = qsum / (bot - top);
+    }
+    G(k) = out;
+    top = bot;
+  }
+  // copy the remapped column over the input, a few levels per trip (loads first)
+  for (int k = 0; k < km; k += 8) {
+    double t[8];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) t[n] = k + n < km ? G(k + n) : 0.0;
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+      if (k + n < km) q1[c0 + (k + n) * sk] = t[n];
+  }
+}
+
+#ifndef FV3_HOSTSIM
+__global__ void __launch_bounds__(MAP_NT) kmap(const MapBatch mb, int km) {
+  extern __shared__ double map_smem[];
+  const fv3_geom &g = c_g;
+  const int f = (int)blockIdx.z, s = (int)blockIdx.y;
+  const int ni = g.nx + mb.iex[f], nj = g.ny + mb.jex[f];
+  const int idx = (int)blockIdx.x * MAP_NT + (int)threadIdx.x;
+  if (idx >= ni * nj) return;
+  const int jr = idx / ni, i = g.halo + (idx - jr * ni), j = g.halo + jr;
+  double *qs = map_smem + threadIdx.x;
+  double *gs = mb.out[f] + O3(s, i, j, 0);
+  const int64_t sk = g.sk;
+  map_chain(g, mb, f, s, i, j, km, [&](int k) -> double & { return qs[k * MAP_NT]; },
+            [&](int k) -> double & { return gs[k * sk]; });
+}
+#endif
+
 }  // namespace
 
 extern "C" {
 
-int fv3_map_single(fv3_ctx *ctx, double *q1, const double *pe1, const double *pe2, const double *qs, int qs_is_2d,
-                   double qmin, int kord, int iv, int i_extra, int j_extra, void *stream) {
+int fv3_map_multi(fv3_ctx *ctx, int n, const int64_t *desc, const double *qmin, int kord, void *stream) {
   const fv3_geom g = ctx->g;
   if (kord < 0) kord = -kord;
   if (kord != 9) {
-    fv3::set_error("fv3_map_single: only kord 9 is implemented");
+    fv3::set_error("fv3_map_multi: only kord 9 is implemented");
     return -1;
   }
-  if (g.nz + 1 > NKMAX) {
-    fv3::set_error("fv3_map_single: nz too large");
+  if (g.nz + 1 > NKMAX || g.nz < 8) {
+    fv3::set_error("fv3_map_multi: nz out of range");
     return -1;
+  }
+  if (n < 1 || n > MAP_MAX) {
+    fv3::set_error("fv3_map_multi: 1..16 fields per call");
+    return -1;
+  }
+  MapBatch mb;
+  mb.n = n;
+  for (int f = 0; f < n; ++f) {
+    const int64_t *d = desc + 8 * f;
+    mb.q1[f] = (double *)d[0];
+    mb.pe1[f] = (const double *)d[1];
+    mb.pe2[f] = (const double *)d[2];
+    mb.qs[f] = (const double *)d[3];
+    mb.qs2d[f] = (int)d[4];
+    mb.iv[f] = (int)d[5];
+    mb.iex[f] = (int)d[6];
+    mb.jex[f] = (int)d[7];
+    mb.qmin[f] = qmin[f];
+    mb.out[f] = fv3::scratch_field(ctx, f);
   }
   const int h = g.halo, km = g.nz;
-  fv3::launch2d(ctx, (cudaStream_t)stream, h, h + g.nx + i_extra, h, h + g.ny + j_extra, FV_LAMBDA(int s, int i, int j) { FV_DEV_GM
-    const int64_t c0 = O3(s, i, j, 0), sk = g.sk;
-    Profile p;
-    double dp1[NKMAX], p1[NKMAX];
-    for (int k = 0; k <= km; ++k) p1[k] = pe1[c0 + k * sk];
-    for (int k = 0; k < km; ++k) {
-      p.a1[k] = q1[c0 + k * sk];
-      dp1[k] = p1[k + 1] - p1[k];
-    }
-    double qsv = 0.0;
-    if (qs != nullptr) qsv = qs_is_2d ? qs[O2(s, i, j)] : qs[c0];
-    remap_profile(p, dp1, km, iv, qsv, qmin);
-    // lagrangian_contributions (map_single.py:21-81); L = absolute source layer
-    int L = 0;
-    double top = pe2[c0];
-    for (int k = 0; k < km; ++k) {
-      const double bot = pe2[c0 + (k + 1) * sk];
-      const double pl = (top - p1[L]) / dp1[L];
-      double out;
-      if (bot <= p1[L + 1]) {
-        const double pr = (bot - p1[L]) / dp1[L];
-        out = p.a2[L] + 0.5 * (p.a4[L] + p.a3[L] - p.a2[L]) * (pr + pl) - p.a4[L] * 1.0 / 3.0 * (pr * (pr + pl) + pl * pl);
-      } else {
-        double qsum = (p1[L + 1] - top) * (p.a2[L] + 0.5 * (p.a4[L] + p.a3[L] - p.a2[L]) * (1.0 + pl) -
-                                           p.a4[L] * 1.0 / 3.0 * (1.0 + pl * (1.0 + pl)));
-        L = L + 1;
-        while (L + 1 <= km && p1[L + 1] < bot) {
-          qsum += dp1[L] * p.a1[L];
-          L = L + 1;
+#ifdef FV3_HOSTSIM
+  (void)stream;
+  for (int f = 0; f < n; ++f) {
+    const int ni = g.nx + mb.iex[f], nj = g.ny + mb.jex[f];
+#ifdef FV3_HOSTSIM_OMP
+#pragma omp parallel for collapse(2) schedule(static)
+#endif
+    for (int s = 0; s < g.n_sub; ++s)
+      for (int j = h; j < h + nj; ++j)
+        for (int i = h; i < h + ni; ++i) {
+          double qa[NKMAX], ga[NKMAX];
+          map_chain(g, mb, f, s, i, j, km, [&](int k) -> double & { return qa[k]; },
+                    [&](int k) -> double & { return ga[k]; });
         }
-        if (L > km - 1) L = km - 1;
-        const double dp = bot - p1[L], esl = dp / dp1[L];
-        qsum += dp * (p.a2[L] + 0.5 * esl * (p.a3[L] - p.a2[L] + p.a4[L] * (1.0 - (2.0 / 3.0) * esl)));
-        out = qsum / (bot - top);
-      }
-      q1[c0 + k * sk] = out;
-      top = bot;
-    }
-  });
-  return fv3::check_launch("fv3_map_single");
+  }
+  return 0;
+#else
+  cudaStream_t st = (cudaStream_t)stream;
+  fv3::activate(ctx, st);
+  const int ncols = (g.nx + 1) * (g.ny + 1);
+  kmap<<<dim3((ncols + MAP_NT - 1) / MAP_NT, g.n_sub, n), MAP_NT, (size_t)(km + 1) * MAP_NT * sizeof(double), st>>>(mb, km);
+  ++fv3::g_launches;
+  return fv3::check_launch("fv3_map_multi");
+#endif
+}
+
+int fv3_map_single(fv3_ctx *ctx, double *q1, const double *pe1, const double *pe2, const double *qs, int qs_is_2d,
+                   double qmin, int kord, int iv, int i_extra, int j_extra, void *stream) {
+  const int64_t d[8] = {(int64_t)q1, (int64_t)pe1, (int64_t)pe2, (int64_t)qs, qs_is_2d, iv, i_extra, j_extra};
+  return fv3_map_multi(ctx, 1, d, &qmin, kord, stream);
 }
 
 int fv3_fillz(fv3_ctx *ctx, double *const *tracers, int nq, const double *dp2, void *stream) {
@@ -243,6 +416,11 @@ int fv3_fillz(fv3_ctx *ctx, double *const *tracers, int nq, const double *dp2, v
   fv3::launch3d(ctx, (cudaStream_t)stream, h, h + g.nx, h, h + g.ny, 0, nq, FV_LAMBDA(int s, int i, int j, int t) { FV_DEV_GM
     double *qf = tracers[t];
     const int64_t c0 = O3(s, i, j, 0), sk = g.sk;
+    {  // a column without negative values comes out unchanged (no fix-ups, zfix == 0): one streaming read, no write
+      bool neg = false;
+      for (int k = 0; k < km; ++k) neg = neg || qf[c0 + k * sk] < 0.0;
+      if (!neg) return;
+    }
     double q[NKMAX], dp[NKMAX], lower_fix[NKMAX], upper_fix[NKMAX], dm[NKMAX], dm_pos[NKMAX];
     bool any_neg = false;
     for (int k = 0; k < km; ++k) {

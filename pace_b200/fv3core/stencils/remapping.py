@@ -1,6 +1,7 @@
 """LagrangianToEulerian — drop-in for fv3core/pace/fv3core/stencils/remapping.py:275-695."""
 from typing import Dict
 
+import numpy as np
 import torch
 
 from ... import constants as c
@@ -31,6 +32,7 @@ class LagrangianToEulerian:
         self._fill = bool(config.fill)
         qf = quantity_factory
         self._pe1, self._pe2, self._pe3, self._pe0 = (qf.zeros(_C3I, "Pa") for _ in range(4))
+        self._pe3v, self._pe0v = qf.zeros(_C3I, "Pa"), qf.zeros(_C3I, "Pa")
         self._dp2, self._pn2 = qf.zeros(_C3, "Pa"), qf.zeros(_C3, "Pa")
         self._kord_tm, self._kord_tr = abs(config.kord_tm), abs(config.kord_tr)
         self._kord_wz, self._kord_mt = config.kord_wz, config.kord_mt
@@ -40,9 +42,16 @@ class LagrangianToEulerian:
         self._tq = torch.tensor([tracers[n].ptr for n in self._tq_names], dtype=torch.int64).to(rt.device)
         self._bound = {n: tracers[n].ptr for n in set(names6) | set(self._tq_names)}
 
-    def _map(self, q, pe1, pe2, kord, iv, qs=None, qs_2d=True, qmin=0.0, i_extra=0, j_extra=0):
-        self._rt.call("fv3_map_single", q.ptr, pe1.ptr, pe2.ptr, qs.ptr if qs is not None else None, int(qs_2d),
-                      float(qmin), int(kord), int(iv), int(i_extra), int(j_extra))
+    @staticmethod
+    def _desc(q, pe1, pe2, iv, qs=None, qs_2d=True, qmin=0.0, i_extra=0, j_extra=0):
+        return ([q.ptr, pe1.ptr, pe2.ptr, qs.ptr if qs is not None else 0, int(qs_2d), int(iv), int(i_extra),
+                 int(j_extra)], float(qmin))
+
+    def _map_batch(self, descs, kord):
+        """MapSingle over several independent fields in one launch (all kord values of a batch are equal: 9)."""
+        d = np.asarray([r for r, _ in descs], dtype=np.int64)
+        qmin = np.asarray([m for _, m in descs], dtype=np.float64)
+        self._rt.call("fv3_map_multi", len(descs), d.ctypes.data, qmin.ctypes.data, int(kord))
 
     def __call__(self, tracers: Dict[str, Quantity], pt, delp, delz, peln, u, v, w, cappa, q_con, q_cld, pkz, pk, pe, hs,
                  ps, wsd, ak, bk, dp1, ptop: float, akap: float, zvir: float, last_step: bool, consv_te: float,
@@ -54,19 +63,20 @@ class LagrangianToEulerian:
         t6 = self._t6.data_ptr()
         rt.call("fv3_remap_prep", t6, q_con.ptr, pt.ptr, cappa.ptr, delp.ptr, delz.ptr, pe.ptr, self._pe1.ptr,
                 self._pe2.ptr, self._dp2.ptr, ps.ptr, self._pn2.ptr, peln.ptr, pk.ptr, float(ptop), float(akap), float(zvir))
-        self._map(pt, peln, self._pn2, self._kord_tm, 1, qmin=self._t_min)
-        for n in self._tq_names:
-            self._map(tracers[n], self._pe1, self._pe2, self._kord_tr, 0)
+        # map_single(pt), mapn_tracer, map_single(w), map_single(delz) (remapping.py:560-612): independent columns of
+        # independent fields, one launch
+        batch = [self._desc(pt, peln, self._pn2, 1, qmin=self._t_min)]
+        batch += [self._desc(tracers[n], self._pe1, self._pe2, 0) for n in self._tq_names]
+        batch += [self._desc(w, self._pe1, self._pe2, -2, qs=wsd), self._desc(delz, self._pe1, self._pe2, 1)]
+        self._map_batch(batch, self._kord_tm)
         if self._fill:
             rt.call("fv3_fillz", self._tq.data_ptr(), self._nq, self._dp2.ptr)
-        self._map(w, self._pe1, self._pe2, self._kord_wz, -2, qs=wsd)
-        self._map(delz, self._pe1, self._pe2, self._kord_wz, 1)
         rt.call("fv3_remap_post", t6, q_con.ptr, pkz.ptr, pt.ptr, cappa.ptr, delp.ptr, delz.ptr, peln.ptr, self._pe0.ptr,
                 self._pn2.ptr, float(zvir))
         rt.call("fv3_remap_pressures", pe.ptr, self._pe0.ptr, self._pe3.ptr, 0)
-        self._map(u, self._pe0, self._pe3, self._kord_mt, -1, j_extra=1)
-        rt.call("fv3_remap_pressures", pe.ptr, self._pe0.ptr, self._pe3.ptr, 1)
-        self._map(v, self._pe0, self._pe3, self._kord_mt, -1, i_extra=1)
+        rt.call("fv3_remap_pressures", pe.ptr, self._pe0v.ptr, self._pe3v.ptr, 1)
+        self._map_batch([self._desc(u, self._pe0, self._pe3, -1, j_extra=1),
+                         self._desc(v, self._pe0v, self._pe3v, -1, i_extra=1)], self._kord_mt)
         dtmp = 0.0
         if last_step:
             if consv_te > CONSV_MIN:
