@@ -143,6 +143,55 @@ FV_HD void map_coef(int L, int km, int iv, double qmin, double am2, double am1, 
   if (iv == 0) posdef_iv0(b1, b2, b3, b4);
 }
 
+
+// k-loops over streamed global operands: body(k, a, b) for k in [kb, ke) ascending (or descending for stream_down),
+// with a(k) = la(k), b(k) = lb(k) requested DEPTH trips before their use and held in a register ring.
+constexpr int STREAM_DEPTH = 8;
+template <class LA, class LB, class B>
+FV_DEV void stream_up(int kb, int ke, LA la, LB lb, B body) {
+  double ra[STREAM_DEPTH], rb[STREAM_DEPTH];
+#pragma unroll
+  for (int n = 0; n < STREAM_DEPTH; ++n) {
+    const int k = kb + n;
+    ra[n] = k < ke ? la(k) : 0.0;
+    rb[n] = k < ke ? lb(k) : 0.0;
+  }
+  for (int k0 = kb; k0 < ke; k0 += STREAM_DEPTH) {
+#pragma unroll
+    for (int n = 0; n < STREAM_DEPTH; ++n) {
+      const int k = k0 + n;
+      if (k < ke) {
+        const double a = ra[n], b = rb[n];
+        const int kn = k + STREAM_DEPTH;
+        ra[n] = kn < ke ? la(kn) : 0.0;
+        rb[n] = kn < ke ? lb(kn) : 0.0;
+        body(k, a, b);
+      }
+    }
+  }
+}
+template <class LA, class B>
+FV_DEV void stream_down(int kb, int ke, LA la, B body) {  // k = ke-1 .. kb
+  double ra[STREAM_DEPTH];
+#pragma unroll
+  for (int n = 0; n < STREAM_DEPTH; ++n) {
+    const int k = ke - 1 - n;
+    ra[n] = k >= kb ? la(k) : 0.0;
+  }
+  for (int k0 = ke - 1; k0 >= kb; k0 -= STREAM_DEPTH) {
+#pragma unroll
+    for (int n = 0; n < STREAM_DEPTH; ++n) {
+      const int k = k0 - n;
+      if (k >= kb) {
+        const double a = ra[n];
+        const int kn = k - STREAM_DEPTH;
+        ra[n] = kn >= kb ? la(kn) : 0.0;
+        body(k, a);
+      }
+    }
+  }
+}
+
 // Inputs are read through the read-only path (FV_LDG) and streamed a few levels ahead of their use: q1 is only
 // written by this chain's final copy, after its last read.
 template <class QS, class GS>
@@ -169,34 +218,34 @@ FV_DEV void map_chain(const fv3_geom &g, const MapBatch &mb, int f, int s, int i
       G(0) = gm;
     }
     double d4 = 0.0;
-#pragma unroll 4
-    for (int k = 1; k < km; ++k) {
-      d4 = dpm / dpk;
-      const double bet = 2.0 + d4 + d4 - gm;
-      qm = (3.0 * (am + d4 * ak) - qm) / bet;
-      gm = d4 / bet;
-      Q(k) = qm;
-      G(k) = gm;
-      if (k + 1 < km) {
-        dpm = dpk;
-        am = ak;
-        p_k = p_k1;
-        p_k1 = P1(k + 2);
-        dpk = p_k1 - p_k;
-        ak = A1(k + 1);
-      }
-    }
+    // trip k consumes pe1[k+2] and a1[k+1] (to set up trip k+1)
+    stream_up(1, km, [&](int k) { return k + 2 <= km ? P1(k + 2) : 0.0; }, [&](int k) { return k + 1 < km ? A1(k + 1) : 0.0; },
+              [&](int k, double p_next, double a_next) {
+                d4 = dpm / dpk;
+                const double bet = 2.0 + d4 + d4 - gm;
+                qm = (3.0 * (am + d4 * ak) - qm) / bet;
+                gm = d4 / bet;
+                Q(k) = qm;
+                G(k) = gm;
+                if (k + 1 < km) {
+                  dpm = dpk;
+                  am = ak;
+                  p_k = p_k1;
+                  p_k1 = p_next;
+                  dpk = p_k1 - p_k;
+                  ak = a_next;
+                }
+              });
     {
       // d4 = delp[km-2] / delp[km-1], ak = a1[km-1], am = a1[km-2], qm = q[km-1], gm = gam[km-1]
       const double a_bot = 1.0 + d4 * (d4 + 1.5);
       Q(km) = (2.0 * d4 * (d4 + 1.0) * ak + am - a_bot * qm) / (d4 * (d4 + 0.5) - a_bot * gm);
     }
     double qn = Q(km);
-#pragma unroll 4
-    for (int k = km - 1; k >= 0; --k) {
-      qn = Q(k) - G(k) * qn;
+    stream_down(0, km, [&](int k) { return G(k); }, [&](int k, double gk) {
+      qn = Q(k) - gk * qn;
       Q(k) = qn;
-    }
+    });
   } else {
     double qsv = 0.0;
     if (mb.qs[f] != nullptr) qsv = mb.qs2d[f] ? mb.qs[f][O2(s, i, j)] : mb.qs[f][c0];
@@ -210,14 +259,13 @@ FV_DEV void map_chain(const fv3_geom &g, const MapBatch &mb, int f, int s, int i
     double grm = dpm / dpk;  // gr[1]
     double qm = (3.0 * (am + ak) - q0) / (2.0 + grm + grm - gm);
     Q(1) = qm;
-#pragma unroll 4
-    for (int k = 2; k < km; ++k) {
+    stream_up(2, km, [&](int k) { return P1(k + 1); }, [&](int k) { return A1(k); }, [&](int k, double p_new, double a_new) {
       dpm = dpk;
       am = ak;
       p_k = p_k1;
-      p_k1 = P1(k + 1);
+      p_k1 = p_new;
       dpk = p_k1 - p_k;  // delp[k]
-      ak = A1(k);
+      ak = a_new;
       const double old_bet = 2.0 + grm + grm - gm;
       gm = grm / old_bet;  // gam[k]
       G(k) = gm;
@@ -230,21 +278,18 @@ FV_DEV void map_chain(const fv3_geom &g, const MapBatch &mb, int f, int s, int i
         Q(km - 1) = (3.0 * (am + ak) - grk * qsv - qm) / (2.0 + grk + grk - gm);
       }
       grm = grk;
-    }
+    });
     Q(km) = qsv;
     double qn = Q(km - 1);
-#pragma unroll 4
-    for (int k = km - 2; k >= 0; --k) {
-      qn = Q(k) - G(k + 1) * qn;
+    stream_down(0, km - 1, [&](int k) { return G(k + 1); }, [&](int k, double gk1) {
+      qn = Q(k) - gk1 * qn;
       Q(k) = qn;
-    }
+    });
   }
   // apply_constraints (:253-337) on the interior interfaces
   {
     double a_m2 = 0.0, a_m1 = A1(0), a_0 = A1(1);
-#pragma unroll 4
-    for (int k = 1; k < km; ++k) {
-      const double a_p1 = k + 1 < km ? A1(k + 1) : 0.0;
+    stream_up(1, km, [&](int k) { return k + 1 < km ? A1(k + 1) : 0.0; }, [&](int) { return 0.0; }, [&](int k, double a_p1, double) {
       const double tmp = a_m1 > a_0 ? a_m1 : a_0, tmp2 = a_m1 < a_0 ? a_m1 : a_0;
       double qk = Q(k);
       if (k == 1 || k == km - 1) {
@@ -266,7 +311,7 @@ FV_DEV void map_chain(const fv3_geom &g, const MapBatch &mb, int f, int s, int i
       a_m2 = a_m1;
       a_m1 = a_0;
       a_0 = a_p1;
-    }
+    });
   }
   // lagrangian_contributions (map_single.py:21-81).  L = absolute source layer.  Sliding register windows around
   // it: layer means w[n] = a1[L-2+n] (n = 0..7) and pressures p[n] = pe1[L+n] (n = 0..4); the element entering a
@@ -330,9 +375,10 @@ FV_DEV void map_chain(const fv3_geom &g, const MapBatch &mb, int f, int s, int i
 __global__ void __launch_bounds__(MAP_NT) kmap(const MapBatch mb, int km) {
   extern __shared__ double map_smem[];
   const fv3_geom &g = c_g;
-  const int f = (int)blockIdx.z, s = (int)blockIdx.y;
+  // field fastest: the chains of one column tile (which share pe1 / pe2) are resident together
+  const int f = (int)blockIdx.x, s = (int)blockIdx.z;
   const int ni = g.nx + mb.iex[f], nj = g.ny + mb.jex[f];
-  const int idx = (int)blockIdx.x * MAP_NT + (int)threadIdx.x;
+  const int idx = (int)blockIdx.y * MAP_NT + (int)threadIdx.x;
   if (idx >= ni * nj) return;
   const int jr = idx / ni, i = g.halo + (idx - jr * ni), j = g.halo + jr;
   double *qs = map_smem + threadIdx.x;
@@ -398,7 +444,7 @@ int fv3_map_multi(fv3_ctx *ctx, int n, const int64_t *desc, const double *qmin, 
   cudaStream_t st = (cudaStream_t)stream;
   fv3::activate(ctx, st);
   const int ncols = (g.nx + 1) * (g.ny + 1);
-  kmap<<<dim3((ncols + MAP_NT - 1) / MAP_NT, g.n_sub, n), MAP_NT, (size_t)(km + 1) * MAP_NT * sizeof(double), st>>>(mb, km);
+  kmap<<<dim3(n, (ncols + MAP_NT - 1) / MAP_NT, g.n_sub), MAP_NT, (size_t)(km + 1) * MAP_NT * sizeof(double), st>>>(mb, km);
   ++fv3::g_launches;
   return fv3::check_launch("fv3_map_multi");
 #endif
