@@ -142,10 +142,11 @@ FV_HD double a2b_point(const fv3_geom &g, const fv3_grid &m, int s, Q q, int i, 
   return 0.5 * (qxx + qyy);
 }
 
-// ---- plane-resident form (plane.h): the reference's three temporaries qx, qy, qout_edges are built ONCE per plane
+// ---- plane-resident form (plane.h): the reference's three temporaries qx, qy, qout_edges are built ONCE per strip
 // in shared memory instead of being re-derived inside every thread.
 //   SQ: qin plane   QX / QY: ppm_volume_mean_x / _y   OUT: B-grid result (tile-edge values first, then the rest)
-// qin / qout are global pointers to the start of the (s, k) plane; each array holds nj * sj doubles.
+// qin is a global pointer to the start of the (s, k) plane; the arrays are shared planes of the block (Block::plane).
+// On return OUT holds the corner rows [ja, jb] of the strip.
 template <class B>
 FV_DEV void a2b_plane(const fv3_geom &g, const fv3_grid &m, int s, const B &b, const double *qin, double *SQ, double *QX,
                      double *QY, double *OUT) {
@@ -153,30 +154,28 @@ FV_DEV void a2b_plane(const fv3_geom &g, const fv3_grid &m, int s, const B &b, c
   const int isc = h, iec = h + g.nx - 1, jsc = h, jec = h + g.ny - 1;
   const bool W = on_west(g, s), E = on_east(g, s), S = on_south(g, s), N = on_north(g, s);
   const int nwi = g.ni - 1, nwj = g.nj - 1;
-  b.par(nwi * nwj, [&](int t) {
-    const int j = t / nwi, i = t - j * nwi;
-    SQ[j * sj + i] = qin[j * sj + i];
-  });
+  const int ja = b.ja, jb = b.jb;
+  b.rect(0, nwi, b.lo(0, h), b.hi(nwj, h), [&](int i, int j) { SQ[j * sj + i] = qin[j * sj + i]; });
   auto q = [&](int ii, int jj) { return SQ[jj * sj + ii]; };
-  // qx on corner columns isc..iec+1, rows jsc-2..jec+2; qy on rows jsc..jec+1, columns isc-2..iec+2; edge values
-  const int nxc = g.nx + 1, nyc = g.ny + 1, nxw = g.nx + 4, nyw = g.ny + 4;
-  b.par(nxc * nyw + nxw * nyc, [&](int t) {
-    if (t < nxc * nyw) {
-      const int jr = t / nxc, i = isc + (t - jr * nxc), j = jsc - 2 + jr;
+  // qx on corner columns isc..iec+1, rows ja-2..jb+1; qy on rows ja..jb, columns isc-2..iec+2
+  const int xj0 = b.lo(jsc - 2, 2), xj1 = b.hi(jec + 3, 2), yj0 = ja, yj1 = jb + 1;
+  const int nxc = g.nx + 1, nxw = g.nx + 4, nxr = xj1 - xj0, nyr = yj1 - yj0;
+  b.par(nxc * nxr + nxw * nyr, [&](int t) {
+    if (t < nxc * nxr) {
+      const int jr = t / nxc, i = isc + (t - jr * nxc), j = xj0 + jr;
       QX[j * sj + i] = a2b_qx(g, m, s, q, i, j);
     } else {
-      const int t2 = t - nxc * nyw;
-      const int jr = t2 / nxw, i = isc - 2 + (t2 - jr * nxw), j = jsc + jr;
+      const int t2 = t - nxc * nxr;
+      const int jr = t2 / nxw, i = isc - 2 + (t2 - jr * nxw), j = yj0 + jr;
       QY[j * sj + i] = a2b_qy(g, m, s, q, i, j);
     }
   });
-  b.par(nxc * nyc, [&](int t) {
-    const int jr = t / nxc, i = isc + (t - jr * nxc), j = jsc + jr;
+  // tile-edge values, one corner row beyond the strip (the rows next to a tile edge read them)
+  b.rect(isc, iec + 2, b.lo(jsc, 1), b.hi(jec + 2, 2), [&](int i, int j) {
     if ((W && i == isc) || (E && i == iec + 1) || (S && j == jsc) || (N && j == jec + 1))
       OUT[j * sj + i] = a2b_edge_value(g, m, s, q, i, j);
   });
-  b.par(nxc * nyc, [&](int t) {
-    const int jr = t / nxc, i = isc + (t - jr * nxc), j = jsc + jr;
+  b.rect(isc, iec + 2, ja, jb + 1, [&](int i, int j) {
     if ((W && i == isc) || (E && i == iec + 1) || (S && j == jsc) || (N && j == jec + 1)) return;
     auto qx = [&](int jj) { return QX[jj * sj + i]; };
     auto qy = [&](int ii) { return QY[j * sj + ii]; };

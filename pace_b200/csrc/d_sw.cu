@@ -57,14 +57,13 @@ FV_HD void bgrid_corner_y(const fv3_geom &g, int s, int &i, int &j) {
 void a2b_ord4_launch(const fv3_ctx *ctx, cudaStream_t st, const double *qin, double *qout, int k0, int k1) {
   const fv3_geom g = ctx->g;
   const fv3_grid m = ctx->m;
-  const int PL = g.nj * g.sj;
-  fv3::launch_planes(ctx, st, k0, k1, 4 * PL, FV_LAMBDA(int s, int k, const fv3::Block &b) { FV_DEV_GM
-    double *SQ = b.sm, *QX = SQ + PL, *QY = QX + PL, *OUT = QY + PL;
+  fv3::launch_planes(ctx, st, k0, k1, 4, FV_LAMBDA(int s, int k, const fv3::Block &b) { FV_DEV_GM
+    double *SQ = b.plane(0), *QX = b.plane(1), *QY = b.plane(2), *OUT = b.plane(3);
     const int64_t ob = O3(s, 0, 0, k);
     fv3::a2b_plane(g, m, s, b, qin + ob, SQ, QX, QY, OUT);
-    const int sj2 = g.sj, nxc = g.nx + 1, h2 = g.halo;
-    b.par(nxc * (g.ny + 1), [&](int t) {
-      const int jr = t / nxc, p = (h2 + jr) * sj2 + h2 + (t - jr * nxc);
+    const int sj2 = g.sj, h2 = g.halo;
+    b.rect(h2, h2 + g.nx + 1, b.ja, b.jtop() + 1, [&](int i, int j) {
+      const int p = j * sj2 + i;
       qout[ob + p] = OUT[p];
     });
   });
@@ -203,17 +202,16 @@ void divergence_damping(fv3_ctx *ctx, cudaStream_t st, const double *u, const do
   }
   // a2b_ord4 of the relative vorticity + Smagorinsky-type diffusion + high-order damping
   // (divergence_damping.py:590-632): one plane-resident kernel, the B-grid vorticity never leaves shared memory
-  const int PL = g.nj * g.sj;
-  fv3::launch_planes(ctx, st, k0, nz, 4 * PL, FV_LAMBDA(int s, int k, const fv3::Block &b) { FV_DEV_GM
-    double *SQ = b.sm, *QX = SQ + PL, *QY = QX + PL, *OUT = QY + PL;
+  fv3::launch_planes(ctx, st, k0, nz, 4, FV_LAMBDA(int s, int k, const fv3::Block &b) { FV_DEV_GM
+    double *SQ = b.plane(0), *QX = b.plane(1), *QY = b.plane(2), *OUT = b.plane(3);
     const int64_t ob = O3(s, 0, 0, k);
     const bool smag = !(dddmp < 1e-5);
     if (smag) fv3::a2b_plane(g, m, s, b, vort_a + ob, SQ, QX, QY, OUT);
     const int sj2 = g.sj, h2 = g.halo;
     const double *rarea_unused = nullptr;
     (void)rarea_unused;
-    b.par2(g.nx + 1, g.ny + 1, [&](int ir, int jr) {
-      const int p = (h2 + jr) * sj2 + h2 + ir;
+    b.rect(h2, h2 + g.nx + 1, b.ja, b.jtop() + 1, [&](int i, int j) {
+      const int p = j * sj2 + i;
       const int64_t o = ob + p;
       double vo;
       if (!smag) {

@@ -51,38 +51,40 @@ FV_DEV void fvtp2d_plane(const fv3_geom &g, const fv3_grid &m, int s, int k, con
   const fv3::Edge1D ex{fv3::on_west(g, s), fv3::on_east(g, s), isc, iec};
   const fv3::Edge1D ey{fv3::on_south(g, s), fv3::on_north(g, s), jsc, jec};
   const int nwi = ied + 1, nwj = jed + 1;
+  // this strip: fluxes on cell rows [ja, jb) and y faces [ja, jb]; q, fx_in and q_j on rows [rl, rh)
+  const int ja = b.ja, jb = b.jb, rl = b.lo(0, h), rh = b.hi(nwj, h);
   {  // operands of the later phases: start their HBM -> L2 transfer now
-    const int pl = g.nj * sj;
-    b.prefetch_l2(cry, pl);
-    b.prefetch_l2(crx, pl);
-    b.prefetch_l2(yfx, pl);
-    b.prefetch_l2(xfx, pl);
-    if (a.xu != a.xfx) b.prefetch_l2(a.xu + ob, pl);
-    if (a.yu != a.yfx) b.prefetch_l2(a.yu + ob, pl);
+    b.prefetch_rows(cry, sj);
+    b.prefetch_rows(crx, sj);
+    b.prefetch_rows(yfx, sj);
+    b.prefetch_rows(xfx, sj);
+    if (a.xu != a.xfx) b.prefetch_rows(a.xu + ob, sj);
+    if (a.yu != a.yfx) b.prefetch_rows(a.yu + ob, sj);
   }
   // 1. load q; 3x3 cube-corner halo blocks as copy_corners_y leaves them
-  b.par2(nwi, nwj, [&](int i, int j) {
+  b.rect(0, nwi, rl, rh, [&](int i, int j) {
     int ii = i, jj = j;
     if ((i < isc || i > iec) && (j < jsc || j > jec)) fv3::corner_y(g, s, ii, jj);
     Q[j * sj + i] = FV_LDG(q + jj * sj + ii);
   });
-  // 2. inner y sweep on q: all columns, faces jsc .. jec+1
-  fv3::ppm_sweep<MORD, false>(b, Q, T, sj, cry, dya, ey, 0, nwi, [&](int p, double val) { A[p] = val; });
+  // 2. inner y sweep on q: all columns, faces ja .. jb
+  fv3::ppm_sweep<MORD, false>(b, Q, T, sj, cry, dya, ey, 0, nwi, ja, jb, [&](int p, double val) { A[p] = val; });
   // 3. cube-corner blocks as copy_corners_x leaves them
   b.par(4 * h * h, [&](int t) {
     const int c = t / (h * h), r = t - c * h * h, a1 = r / h, b1 = r - a1 * h;
     const int i = (c & 1) ? iec + 1 + a1 : a1, j = (c & 2) ? jec + 1 + b1 : b1;
+    if (j < rl || j >= rh) return;
     int ii = i, jj = j;
     fv3::corner_x(g, s, ii, jj);
     Q[j * sj + i] = q[jj * sj + ii];
   });
-  // 4. inner x sweep on q: all rows, faces isc .. iec+1
-  fv3::ppm_sweep<MORD, true>(b, Q, T, sj, crx, dxa, ex, 0, nwj, [&](int p, double val) { B[p] = val; });
-  // 5. transverse updates: q_i (into Q, compute rows) and q_j (into D, compute columns)
-  b.par2(nwi, nwj, [&](int i, int j) {
+  // 4. inner x sweep on q: resident rows, faces isc .. iec+1
+  fv3::ppm_sweep<MORD, true>(b, Q, T, sj, crx, dxa, ex, rl, rh - rl, isc, iec + 1, [&](int p, double val) { B[p] = val; });
+  // 5. transverse updates: q_i (into Q, owned rows) and q_j (into D, compute columns of the resident rows)
+  b.rect(0, nwi, rl, rh, [&](int i, int j) {
     const int p = j * sj + i;
     const double qv = Q[p], ar = FV_LDG(area + p);
-    if (j >= jsc && j <= jec) {
+    if (j >= ja && j < jb) {
       const double y0 = FV_LDG(yfx + p), y1 = FV_LDG(yfx + p + sj);
       const double f0 = y0 * A[p], f1 = y1 * A[p + sj];
       Q[p] = (qv * ar + f0 - f1) / (ar + y0 - y1);
@@ -93,29 +95,31 @@ FV_DEV void fvtp2d_plane(const fv3_geom &g, const fv3_grid &m, int s, int k, con
       D[p] = (qv * ar + f0 - f1) / (ar + x0 - x1);
     }
   });
-  // 6. outer x sweep on q_i (compute rows) -> x flux, in place over fx_in
+  // 6. outer x sweep on q_i (owned rows) -> x flux, in place over fx_in
   const double *xu = a.xu + ob, *yu = a.yu + ob;
-  fv3::ppm_sweep<MORD, true>(b, Q, T, sj, crx, dxa, ex, jsc, ny,
+  fv3::ppm_sweep<MORD, true>(b, Q, T, sj, crx, dxa, ex, ja, jb - ja, isc, iec + 1,
                              [&](int p, double val) { B[p] = 0.5 * (val + B[p]) * FV_LDG(xu + p); });
   // 7. outer y sweep on q_j (compute columns) -> y flux, in place over fy_in
-  fv3::ppm_sweep<MORD, false>(b, D, T, sj, cry, dya, ey, isc, nx,
+  fv3::ppm_sweep<MORD, false>(b, D, T, sj, cry, dya, ey, isc, nx, ja, jb,
                               [&](int p, double val) { A[p] = 0.5 * (val + A[p]) * FV_LDG(yu + p); });
 }
 
 // ---- plane-resident del-n fluxes (DelnFlux / DelnFluxNoSG, delnflux.py:59-238,1164-1261) ------------------------
 // D2: the field being differenced (damp * q, then the Laplacians of the previous fluxes), FX / FY: its fluxes.
-// All nord iterations run in shared memory; on return FX / FY hold fx2 / fy2 on the interface domain
-// [isc..iec+1] x [jsc..jec(+1)].  q points at the global (s, k) plane.
+// All nord iterations run in shared memory; on return FX / FY hold fx2 / fy2 on the strip's part of the interface
+// domain: x fluxes on rows [ja, jb), y fluxes on faces [ja, jb].  q points at the global (s, k) plane.  An iteration
+// whose results reach nt cells beyond the compute domain is evaluated nt rows beyond the strip.
 FV_DEV void delnflux_plane(const fv3_geom &g, const fv3_grid &m, int s, const fv3::Block &b, const double *q, double dk,
                           bool hi, int nmax, bool copy_q, double *D2, double *FX, double *FY) {
-  const int sj = g.sj, h = g.halo, nx = g.nx, ny = g.ny;
-  const int isc = h, jsc = h;
+  const int sj = g.sj, h = g.halo, nx = g.nx;
+  const int isc = h;
+  const int ja = b.ja, jb = b.jb;
   const int64_t o2b = O2(s, 0, 0);
   const double *del6_u = m.del6_u + o2b, *del6_v = m.del6_v + o2b, *rarea = m.rarea + o2b;
   const int r = hi ? nmax : 0;
-  // d2 = damp * q on cells [isc-r-1 .. iec+1+r] x [jsc-r-1 .. jec+1+r]
-  b.par2(nx + 2 * r + 2, ny + 2 * r + 2, [&](int ir, int jr) {
-    const int p = (jsc - r - 1 + jr) * sj + isc - r - 1 + ir;
+  // d2 = damp * q on cells [isc-r-1 .. iec+1+r] x [ja-r-1 .. jb+r]
+  b.rect(isc - r - 1, isc + nx + r + 1, ja - r - 1, jb + r + 1, [&](int i, int j) {
+    const int p = j * sj + i;
     const double v = q[p];
     D2[p] = copy_q ? v : dk * v;
   });
@@ -127,28 +131,28 @@ FV_DEV void delnflux_plane(const fv3_geom &g, const fv3_grid &m, int s, const fv
     if (hi) fv3::corner_y(g, s, ii, jj);
     return D2[jj * sj + ii];
   };
-  b.par2(nx + 2 * r + 1, ny + 2 * r + 1, [&](int ir, int jr) {
-    const int i = isc - r + ir, j = jsc - r + jr, p = j * sj + i;
-    if (jr < ny + 2 * r) FX[p] = del6_v[p] * (d2x(i - 1, j) - d2x(i, j));
-    if (ir < nx + 2 * r) FY[p] = del6_u[p] * (d2y(i, j - 1) - d2y(i, j));
+  b.rect(isc - r, isc + nx + r + 1, ja - r, jb + r + 1, [&](int i, int j) {
+    const int p = j * sj + i;
+    if (j < jb + r) FX[p] = del6_v[p] * (d2x(i - 1, j) - d2x(i, j));
+    if (i < isc + nx + r) FY[p] = del6_u[p] * (d2y(i, j - 1) - d2y(i, j));
   });
   if (!hi) return;
   for (int n = 0; n < nmax; ++n) {
     const int nt = nmax - 1 - n;
-    b.par2(nx + 2 * nt + 2, ny + 2 * nt + 2, [&](int ir, int jr) {
-      const int p = (jsc - nt - 1 + jr) * sj + isc - nt - 1 + ir;
+    b.rect(isc - nt - 1, isc + nx + nt + 1, ja - nt - 1, jb + nt + 1, [&](int i, int j) {
+      const int p = j * sj + i;
       D2[p] = (FX[p] - FX[p + 1] + FY[p] - FY[p + sj]) * rarea[p];
     });
-    b.par2(nx + 2 * nt + 1, ny + 2 * nt + 1, [&](int ir, int jr) {
-      const int i = isc - nt + ir, j = jsc - nt + jr, p = j * sj + i;
-      int ia = i - 1, ja = j, ib = i, jb = j;
-      fv3::corner_x(g, s, ia, ja);
-      fv3::corner_x(g, s, ib, jb);
-      if (jr < ny + 2 * nt) FX[p] = -del6_v[p] * (D2[ja * sj + ia] - D2[jb * sj + ib]);
-      ia = i, ja = j - 1, ib = i, jb = j;
-      fv3::corner_y(g, s, ia, ja);
-      fv3::corner_y(g, s, ib, jb);
-      if (ir < nx + 2 * nt) FY[p] = -del6_u[p] * (D2[ja * sj + ia] - D2[jb * sj + ib]);
+    b.rect(isc - nt, isc + nx + nt + 1, ja - nt, jb + nt + 1, [&](int i, int j) {
+      const int p = j * sj + i;
+      int ia = i - 1, jaa = j, ib = i, jbb = j;
+      fv3::corner_x(g, s, ia, jaa);
+      fv3::corner_x(g, s, ib, jbb);
+      if (j < jb + nt) FX[p] = -del6_v[p] * (D2[jaa * sj + ia] - D2[jbb * sj + ib]);
+      ia = i, jaa = j - 1, ib = i, jbb = j;
+      fv3::corner_y(g, s, ia, jaa);
+      fv3::corner_y(g, s, ib, jbb);
+      if (i < isc + nx + nt) FY[p] = -del6_u[p] * (D2[jaa * sj + ia] - D2[jbb * sj + ib]);
     });
   }
 }
@@ -159,18 +163,18 @@ int fvtp2d_launch(const fv3_ctx *ctx, cudaStream_t st, PlaneArgs a, double *fx, 
                   const double *damp, const double *nord, int nmax, const double *mass) {
   const fv3_geom g = ctx->g;
   const fv3_grid m = ctx->m;
-  const int PL = g.nj * g.sj;
-  return fv3::launch_planes(ctx, st, 0, nk, FVTP_PLANES * PL, FV_LAMBDA(int s, int k, const fv3::Block &b) { FV_DEV_GM
-    double *Q = b.sm, *A = Q + PL, *B = A + PL, *D = B + PL, *T = D + PL;
+  return fv3::launch_planes(ctx, st, 0, nk, FVTP_PLANES, FV_LAMBDA(int s, int k, const fv3::Block &b) { FV_DEV_GM
+    double *Q = b.plane(0), *A = b.plane(1), *B = b.plane(2), *D = b.plane(3), *T = b.plane(4);
     const int64_t ob = O3(s, 0, 0, k);
-    if (mode == 2) b.prefetch_l2(mass + ob, PL);
+    const int sj = g.sj, h = g.halo, nx = g.nx;
+    if (mode == 2) b.prefetch_rows(mass + ob, sj);
     fvtp2d_plane<MORD>(g, m, s, k, b, a, Q, A, B, D, T);
-    const int sj = g.sj, h = g.halo, nx = g.nx, ny = g.ny;
+    const int ja = b.ja, jb = b.jb, jt = b.jtop();
     if (mode == 0) {
-      b.par2(nx + 1, ny + 1, [&](int ir, int jr) {
-        const int p = (h + jr) * sj + h + ir;
-        if (jr < ny) fx[ob + p] = B[p];
-        if (ir < nx) fy[ob + p] = A[p];
+      b.rect(h, h + nx + 1, ja, jt + 1, [&](int i, int j) {
+        const int p = j * sj + i;
+        if (j < jb) fx[ob + p] = B[p];
+        if (i < h + nx) fy[ob + p] = A[p];
       });
       return;
     }
@@ -178,14 +182,14 @@ int fvtp2d_launch(const fv3_ctx *ctx, cudaStream_t st, PlaneArgs a, double *fx, 
     const double dk = damp[k];
     delnflux_plane(g, m, s, b, a.q + ob, dk, nord[k] > 0, nmax, mode == 2, Q, D, T);
     const double *ms = mass + ob;
-    b.par2(nx + 1, ny + 1, [&](int ir, int jr) {
-      const int p = (h + jr) * sj + h + ir;
+    b.rect(h, h + nx + 1, ja, jt + 1, [&](int i, int j) {
+      const int p = j * sj + i;
       if (mode == 1) {
-        if (jr < ny) fx[ob + p] = B[p] + D[p];
-        if (ir < nx) fy[ob + p] = A[p] + T[p];
+        if (j < jb) fx[ob + p] = B[p] + D[p];
+        if (i < h + nx) fy[ob + p] = A[p] + T[p];
       } else {
-        if (jr < ny) fx[ob + p] = B[p] + 0.5 * dk * (ms[p - 1] + ms[p]) * D[p];
-        if (ir < nx) fy[ob + p] = A[p] + 0.5 * dk * (ms[p - sj] + ms[p]) * T[p];
+        if (j < jb) fx[ob + p] = B[p] + 0.5 * dk * (ms[p - 1] + ms[p]) * D[p];
+        if (i < h + nx) fy[ob + p] = A[p] + 0.5 * dk * (ms[p - sj] + ms[p]) * T[p];
       }
     });
   });
@@ -203,16 +207,15 @@ int fv3_delnflux_nosg(fv3_ctx *ctx, const double *q, double *fx2, double *fy2, c
   }
   const fv3_geom g = ctx->g;
   const fv3_grid m = ctx->m;
-  const int PL = g.nj * g.sj;
-  int rc = fv3::launch_planes(ctx, (cudaStream_t)stream, 0, nk, 3 * PL, FV_LAMBDA(int s, int k, const fv3::Block &b) { FV_DEV_GM
-    double *D2 = b.sm, *FX = D2 + PL, *FY = FX + PL;
+  int rc = fv3::launch_planes(ctx, (cudaStream_t)stream, 0, nk, 3, FV_LAMBDA(int s, int k, const fv3::Block &b) { FV_DEV_GM
+    double *D2 = b.plane(0), *FX = b.plane(1), *FY = b.plane(2);
     const int64_t ob = O3(s, 0, 0, k);
     delnflux_plane(g, m, s, b, q + ob, damp_col[k], nord_col[k] > 0, nmax, false, D2, FX, FY);
-    const int sj = g.sj, h = g.halo, nx = g.nx, ny = g.ny;
-    b.par2(nx + 1, ny + 1, [&](int ir, int jr) {
-      const int p = (h + jr) * sj + h + ir;
-      if (jr < ny) fx2[ob + p] = FX[p];
-      if (ir < nx) fy2[ob + p] = FY[p];
+    const int sj = g.sj, h = g.halo, nx = g.nx;
+    b.rect(h, h + nx + 1, b.ja, b.jtop() + 1, [&](int i, int j) {
+      const int p = j * sj + i;
+      if (j < b.jb) fx2[ob + p] = FX[p];
+      if (i < h + nx) fy2[ob + p] = FY[p];
     });
   });
   if (rc) return rc;
@@ -266,28 +269,36 @@ int fv3_tracer_subcycle(fv3_ctx *ctx, double *const *tracers, int nq, double *dp
     fv3::set_error("fv3_tracer_subcycle: only hord_tr = 8 is implemented");
     return -1;
   }
-  const int PL = g.nj * g.sj;
-  int rc = fv3::launch_planes(ctx, (cudaStream_t)stream, 0, g.nz, FVTP_PLANES * PL, FV_LAMBDA(int s, int k, const fv3::Block &b) { FV_DEV_GM
-    double *Q = b.sm, *A = Q + PL, *B = A + PL, *D = B + PL, *T = D + PL;
+  if (nq > 16) {
+    fv3::set_error("fv3_tracer_subcycle: at most 16 tracers");
+    return -1;
+  }
+  const fv3::StripGeom sg = fv3::strip_geometry(g, FVTP_PLANES);
+  double *side0 = fv3::scratch_field(ctx, 0);
+  const int64_t side_stride = g.ss * g.n_sub;
+  int rc = fv3::launch_planes(ctx, (cudaStream_t)stream, 0, g.nz, FVTP_PLANES, FV_LAMBDA(int s, int k, const fv3::Block &b) { FV_DEV_GM
+    double *Q = b.plane(0), *A = b.plane(1), *B = b.plane(2), *D = b.plane(3), *T = b.plane(4);
     const int sj = g.sj, h = g.halo, nx = g.nx;
     const int64_t ob = O3(s, 0, 0, k), o2b = O2(s, 0, 0);
     const double *rarea = m.rarea + o2b;
-    b.prefetch_l2(dp1 + ob, PL);
+    b.prefetch_rows(dp1 + ob, sj);
     for (int n = 0; n < nq; ++n) {
       double *q = tracers[n];
-      if (n + 1 < nq) b.prefetch_l2(tracers[n + 1] + ob, PL);
+      if (n + 1 < nq) b.prefetch_rows(tracers[n + 1] + ob, sj);
       const PlaneArgs pa{q, cx, cy, xfx, yfx, mfx, mfy};
       fvtp2d_plane<8>(g, m, s, k, b, pa, Q, A, B, D, T);
-      b.par(nx * g.ny, [&](int t) {
-        const int jr = t / nx, p = (h + jr) * sj + h + (t - jr * nx);
+      b.rect(h, h + nx, b.ja, b.jb, [&](int i, int j) {
+        const int p = j * sj + i;
         const int64_t o = ob + p;
         const double d1 = dp1[o];
         const double d2 = d1 + (mfx[o] - mfx[o + 1] + mfy[o] - mfy[o + sj]) * rarea[p];
-        q[o] = (q[o] * d1 + (B[p] - B[p + 1] + A[p] - A[p + sj]) * rarea[p]) / d2;
+        // rows another strip of this plane reads as halo are parked in a side buffer (in-place update)
+        const bool parked = (j < b.ja + h && b.ja > h) || (j >= b.jb - h && !b.last);
+        (parked ? side0 + n * side_stride : q)[o] = (q[o] * d1 + (B[p] - B[p + 1] + A[p] - A[p + sj]) * rarea[p]) / d2;
       });
     }
-    b.par(nx * g.ny, [&](int t) {
-      const int jr = t / nx, p = (h + jr) * sj + h + (t - jr * nx);
+    b.rect(h, h + nx, b.ja, b.jb, [&](int i, int j) {
+      const int p = j * sj + i;
       const int64_t o = ob + p;
       const double d1 = dp1[o];
       const double d2 = d1 + (mfx[o] - mfx[o + 1] + mfy[o] - mfy[o + sj]) * rarea[p];
@@ -300,6 +311,15 @@ int fv3_tracer_subcycle(fv3_ctx *ctx, double *const *tracers, int nq, double *dp
     });
   });
   if (rc) return rc;
+  if (sg.ns > 1) {
+    // parked rows (3 either side of every interior strip boundary) back into the tracers
+    const int h = g.halo, R = sg.rows_per_strip;
+    fv3::launch3d(ctx, (cudaStream_t)stream, h, h + g.nx, 0, 2 * h * (sg.ns - 1), 0, g.nz, FV_LAMBDA(int s, int i, int jj, int k) { FV_DEV_GM
+      const int h2 = g.halo, bnd = jj / (2 * h2), j = h2 + (bnd + 1) * R - h2 + (jj - bnd * 2 * h2);
+      const int64_t o = O3(s, i, j, k);
+      for (int n = 0; n < nq; ++n) tracers[n][o] = side0[n * side_stride + o];
+    });
+  }
   return fv3::check_launch("fv3_tracer_subcycle");
 }
 

@@ -22,28 +22,24 @@ int fv3_nh_p_grad(fv3_ctx *ctx, double *u, double *v, double *pp, double *gz, do
   double *wk1 = fv3::scratch_field(ctx, 19);
   const double top_value = pow(ptop, akap);  // host libm, as `ptop ** akap` in the reference (:219)
   // four A->B interpolations (nh_p_grad.py:221-224) + set_k0 (:11-20): one plane-resident kernel per level
-  const int PL = g.nj * g.sj;
-  int rc = fv3::launch_planes(ctx, st, 0, nz + 1, 4 * PL, FV_LAMBDA(int s, int k, const fv3::Block &b) { FV_DEV_GM
-    double *SQ = b.sm, *QX = SQ + PL, *QY = QX + PL, *OUT = QY + PL;
+  int rc = fv3::launch_planes(ctx, st, 0, nz + 1, 4, FV_LAMBDA(int s, int k, const fv3::Block &b) { FV_DEV_GM
+    double *SQ = b.plane(0), *QX = b.plane(1), *QY = b.plane(2), *OUT = b.plane(3);
     const int64_t ob = O3(s, 0, 0, k);
-    const int sj2 = g.sj, nxc = g.nx + 1, nyc = g.ny + 1, h2 = g.halo;
+    const int sj2 = g.sj, h2 = g.halo;
     auto store = [&](double *dst) {
-      b.par(nxc * nyc, [&](int t) {
-        const int jr = t / nxc, p = (h2 + jr) * sj2 + h2 + (t - jr * nxc);
+      b.rect(h2, h2 + g.nx + 1, b.ja, b.jtop() + 1, [&](int i, int j) {
+        const int p = j * sj2 + i;
         dst[ob + p] = OUT[p];
       });
     };
     auto fill = [&](double *dst, double value) {
-      b.par(nxc * nyc, [&](int t) {
-        const int jr = t / nxc, p = (h2 + jr) * sj2 + h2 + (t - jr * nxc);
-        dst[ob + p] = value;
-      });
+      b.rect(h2, h2 + g.nx + 1, b.ja, b.jtop() + 1, [&](int i, int j) { dst[ob + j * sj2 + i] = value; });
     };
     if (k >= 1) {
-      b.prefetch_l2(pp + ob, PL);
-      b.prefetch_l2(pk3 + ob, PL);
+      b.prefetch_rows(pp + ob, sj2);
+      b.prefetch_rows(pk3 + ob, sj2);
     }
-    if (k < nz) b.prefetch_l2(delp + ob, PL);
+    if (k < nz) b.prefetch_rows(delp + ob, sj2);
     fv3::a2b_plane(g, m, s, b, gz + ob, SQ, QX, QY, OUT);
     store(gzb);
     if (k >= 1) {

@@ -1,23 +1,40 @@
-// Plane-resident kernels: one CTA owns one horizontal (subdomain, level) plane — (nx+7) x (ny+7) points, 40 KB per
-// fp64 field at C128 layout (2,2) — stages it in shared memory and runs a whole multi-sweep stage on it as a
-// sequence of block-wide phases.  Every input plane is read from HBM once, intermediates (inner-sweep fluxes,
-// transversely advected fields, edge values) never leave the SM, and no thread recomputes a neighbour's value.
+// Plane-resident kernels: a CTA owns a strip of rows [ja, jb) of one horizontal (subdomain, level) plane, stages it
+// — with the 3 halo rows either side that the widest sweep needs — in shared memory and runs a whole multi-sweep
+// stage on it as a sequence of block-wide phases.  Every input row is read from HBM once per strip, intermediates
+// (inner-sweep fluxes, transversely advected fields, edge values) never leave the SM, and no thread recomputes a
+// neighbour's value.  The number of strips per plane is the smallest that lets TWO CTAs share an SM (each CTA's
+// barriers and global-load waits are covered by the other's arithmetic); at C128 layout (2,2) that is 2 strips of 32
+// rows (39 resident rows of 72 doubles = 22 KB per field).  Rows shared by two strips are computed by both (6 of 38
+// rows of the inner sweeps); every output row is stored by exactly one strip.
 //
-//   launch_planes(ctx, st, k0, k1, smem_doubles, f)   f(s, k, Block&) runs once per plane
-//   Block::par(n, g)                                   g(t) for t in [0, n), then a block barrier
+//   launch_planes(ctx, st, k0, k1, n_planes, f)   f(s, k, Block&) runs once per (plane, strip)
+//   Block::plane(n)                               n-th shared plane, addressed [j * sj + i] like a global plane
+//   Block::rect(i0, i1, j0, j1, g)                g(i, j) over the rectangle, then a block barrier
+//   Block::lo(j0, e) / hi(j1, e)                  row range [j0, j1) clipped to [ja - e, jb + e)
 //
 // Under -DFV3_HOSTSIM (g++, tests only) a "block" is a plain loop, so the same phase code runs on the CPU.
 #pragma once
+#include <cstdlib>
 #include <vector>
 
 #include "common.h"
 
 namespace fv3 {
 
-constexpr int PLANE_THREADS = 1024;
+constexpr int PLANE_THREADS = 512;
+constexpr int PLANE_SMEM_BUDGET = (233472 / 2) - 1024;  // bytes per CTA for two CTAs per SM (228 KB, 1 KB reserved each)
 
 struct Block {
   double *sm;
+  int pl, off;  // doubles per shared plane; r0 * sj
+  int ja, jb;   // owned rows: results on cell rows [ja, jb), y-faces / corner rows [ja, jb]
+  int r0, r1;   // resident rows [r0, r1)
+  bool last;    // jb is the top of the compute domain (this strip also stores face / corner row jb)
+
+  FV_HD double *plane(int n) const { return sm + (int64_t)n * pl - off; }
+  FV_HD int jtop() const { return last ? jb : jb - 1; }  // last face / corner row this strip stores
+  FV_HD int lo(int j0, int e) const { return j0 > ja - e ? j0 : ja - e; }
+  FV_HD int hi(int j1, int e) const { return j1 < jb + e ? j1 : jb + e; }
 #ifdef FV3_HOSTSIM
   void prefetch_l2(const double *, int) const {}
   template <class F>
@@ -30,19 +47,8 @@ struct Block {
     for (int jr = 0; jr < nrows; ++jr)
       for (int ir = 0; ir < w; ++ir) f(ir, jr);
   }
-  // as par2, with the global-memory operands of a point fetched by `load(ir, jr, v)` into NV registers before
-  // `comp(ir, jr, v)` runs
-  template <int NV, class L, class C>
-  void par2_pre(int w, int nrows, L load, C comp) const {
-    for (int jr = 0; jr < nrows; ++jr)
-      for (int ir = 0; ir < w; ++ir) {
-        double v[NV];
-        load(ir, jr, v);
-        comp(ir, jr, v);
-      }
-  }
 #else
-  // One bulk L2 prefetch (cp.async.bulk.prefetch.L2) of n contiguous doubles — a whole (s, k) plane of a field is
+  // One bulk L2 prefetch (cp.async.bulk.prefetch.L2) of n contiguous doubles — the resident rows of a field are
   // contiguous in HBM — issued by one thread: operands of later phases are pulled into L2 while the CTA computes.
   __device__ __forceinline__ void prefetch_l2(const double *p, int n) const {
     if (threadIdx.x == 0)
@@ -65,90 +71,105 @@ struct Block {
     }
     __syncthreads();
   }
-  // Software-pipelined form: each thread first issues the global loads of 2 or 4 of its points (independent
-  // LDG.NC requests in flight; out-of-range slots re-load the first point, results unused), then computes them.  With one CTA per SM (shared memory bound) this is what hides
-  // the L2 / HBM latency that the barrier-separated phases would otherwise expose.
-  template <int NV, class L, class C>
-  __device__ __forceinline__ void par2_pre(int w, int nrows, L load, C comp) const {
-    const int n = w * nrows, nt = blockDim.x;
-    const float inv = 1.0f / (float)w;
-    if (NV >= 4) {
-      for (int t0 = threadIdx.x; t0 < n; t0 += 2 * nt) {
-        const int t1 = t0 + nt;
-        const bool h1 = t1 < n;
-        const int j0 = (int)(((float)t0 + 0.5f) * inv), i0 = t0 - j0 * w;
-        const int j1 = h1 ? (int)(((float)t1 + 0.5f) * inv) : j0, i1 = h1 ? t1 - j1 * w : i0;
-        double v0[NV], v1[NV];
-        load(i0, j0, v0);
-        load(i1, j1, v1);
-        comp(i0, j0, v0);
-        if (h1) comp(i1, j1, v1);
-      }
-    } else {
-      for (int t0 = threadIdx.x; t0 < n; t0 += 4 * nt) {
-        const int t1 = t0 + nt, t2 = t1 + nt, t3 = t2 + nt;
-        const bool h1 = t1 < n, h2 = t2 < n, h3 = t3 < n;
-        const int j0 = (int)(((float)t0 + 0.5f) * inv), i0 = t0 - j0 * w;
-        const int j1 = h1 ? (int)(((float)t1 + 0.5f) * inv) : j0, i1 = h1 ? t1 - j1 * w : i0;
-        const int j2 = h2 ? (int)(((float)t2 + 0.5f) * inv) : j0, i2 = h2 ? t2 - j2 * w : i0;
-        const int j3 = h3 ? (int)(((float)t3 + 0.5f) * inv) : j0, i3 = h3 ? t3 - j3 * w : i0;
-        double v0[NV], v1[NV], v2[NV], v3[NV];
-        load(i0, j0, v0);
-        load(i1, j1, v1);
-        load(i2, j2, v2);
-        load(i3, j3, v3);
-        comp(i0, j0, v0);
-        if (h1) comp(i1, j1, v1);
-        if (h2) comp(i2, j2, v2);
-        if (h3) comp(i3, j3, v3);
-      }
-    }
-    __syncthreads();
-  }
 #endif
+  // f(i, j) for i in [i0, i1), j in [j0, j1)
+  template <class F>
+  FV_DEV void rect(int i0, int i1, int j0, int j1, F f) const {
+    par2(i1 > i0 ? i1 - i0 : 0, j1 > j0 ? j1 - j0 : 0, [&](int ir, int jr) { f(i0 + ir, j0 + jr); });
+  }
+  // resident rows of the global plane starting at `plane0`
+  FV_DEV void prefetch_rows(const double *plane0, int sj) const { prefetch_l2(plane0 + r0 * sj, (r1 - r0) * sj); }
 };
+
+struct StripGeom {
+  int ns, rows_per_strip, res_rows;  // strips per plane, owned rows per strip, resident rows per strip
+};
+
+// strips per plane for a kernel with n_planes shared planes; ns == 0: does not fit
+inline StripGeom strip_geometry(const fv3_geom &g, int n_planes) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char *e = getenv("FV3_FORCE_STRIPS");  // tests: exercise the strip logic on small subdomains
+    forced = e ? atoi(e) : 0;
+  }
+  StripGeom sg{0, 0, 0};
+  for (int ns = forced > 0 ? forced : 1; ns <= g.ny; ++ns) {
+    const int r = (g.ny + ns - 1) / ns, res = (r + 2 * g.halo + 1 < g.nj) ? r + 2 * g.halo + 1 : g.nj;
+    if (r < 4) break;
+    const int64_t bytes = (int64_t)n_planes * res * g.sj * 8;
+    if (forced > 0 || bytes <= PLANE_SMEM_BUDGET) {
+      sg = StripGeom{(g.ny + r - 1) / r, r, res};
+      break;
+    }
+  }
+  return sg;
+}
+
+FV_HD Block make_block(const fv3_geom &g, double *sm, int strip, int rows_per_strip, int res_rows) {
+  Block b;
+  b.sm = sm;
+  const int jsc = g.halo, jend = g.halo + g.ny;
+  b.ja = jsc + strip * rows_per_strip;
+  b.jb = b.ja + rows_per_strip < jend ? b.ja + rows_per_strip : jend;
+  b.last = b.jb == jend;
+  b.r0 = b.ja - g.halo;
+  b.r1 = b.jb + g.halo + 1 < g.nj ? b.jb + g.halo + 1 : g.nj;
+  b.pl = res_rows * g.sj;
+  b.off = b.r0 * g.sj;
+  return b;
+}
 
 #ifndef FV3_HOSTSIM
 template <class F>
-__global__ void __launch_bounds__(PLANE_THREADS) kplane(F f, int k0) {
+__global__ void __launch_bounds__(PLANE_THREADS, 2) kplane(F f, int k0, int rows_per_strip, int res_rows) {
   extern __shared__ double plane_smem[];
-  Block b{plane_smem};
+  const Block b = make_block(c_g, plane_smem, (int)blockIdx.z, rows_per_strip, res_rows);
   f((int)blockIdx.y, k0 + (int)blockIdx.x, b);
 }
 #endif
 
 template <class F>
-inline int launch_planes(const fv3_ctx *ctx, cudaStream_t st, int k0, int k1, int smem_doubles, F f) {
+inline int launch_planes(const fv3_ctx *ctx, cudaStream_t st, int k0, int k1, int n_planes, F f) {
   if (k1 <= k0) return 0;
+  const StripGeom sg = strip_geometry(ctx->g, n_planes);
+  if (sg.ns == 0) {
+    set_error("launch_planes: no strip decomposition of the plane fits in shared memory");
+    return -1;
+  }
+  const size_t doubles = (size_t)n_planes * sg.res_rows * ctx->g.sj;
 #ifdef FV3_HOSTSIM
   (void)st;
   const int n_sub = ctx->g.n_sub;
+  const fv3_geom gg = ctx->g;
 #ifdef FV3_HOSTSIM_OMP
 #pragma omp parallel
 #endif
   {
-    std::vector<double> sm((size_t)smem_doubles);
-    Block b{sm.data()};
+    std::vector<double> sm(doubles);
 #ifdef FV3_HOSTSIM_OMP
 #pragma omp for collapse(2) schedule(static)
 #endif
     for (int s = 0; s < n_sub; ++s)
-      for (int k = k0; k < k1; ++k) f(s, k, b);
+      for (int k = k0; k < k1; ++k)
+        for (int z = 0; z < sg.ns; ++z) {
+          const Block b = make_block(gg, sm.data(), z, sg.rows_per_strip, sg.res_rows);
+          f(s, k, b);
+        }
   }
   return 0;
 #else
   activate(ctx, st);
-  const size_t bytes = (size_t)smem_doubles * sizeof(double);
+  const size_t bytes = doubles * sizeof(double);
   static size_t configured = 0;  // one per template instantiation (= per kernel)
   if (bytes > configured) {
     cudaError_t e = cudaFuncSetAttribute(kplane<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) {
-      set_error("launch_planes: plane does not fit in shared memory (subdomain too large for a plane-resident kernel)");
+      set_error("launch_planes: strip does not fit in shared memory");
       return (int)e;
     }
     configured = bytes;
   }
-  kplane<<<dim3(k1 - k0, ctx->g.n_sub), PLANE_THREADS, bytes, st>>>(f, k0);
+  kplane<<<dim3(k1 - k0, ctx->g.n_sub, sg.ns), PLANE_THREADS, bytes, st>>>(f, k0, sg.rows_per_strip, sg.res_rows);
   ++g_launches;
   return 0;
 #endif

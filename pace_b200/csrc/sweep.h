@@ -13,17 +13,21 @@ namespace fv3 {
 
 // Qs: values, Ts: staging plane (same layout).  XDIR: sweep along i (stride 1) on lines j in [l0, l0+nl), else along j
 // (stride sj) on lines i in [l0, l0+nl).  cg: Courant numbers, dxg: cell widths (global planes, same offsets).
-// fin(p, value): what to do with the interface value at plane offset p.
+// Interface values are produced for the faces [f0, f1] of every line (the whole line: e.start .. e.end + 1; a strip
+// sweeping along j passes its own face rows).  fin(p, value): what to do with the value at plane offset p.
 template <int MORD, bool XDIR, class Fin>
 FV_DEV void ppm_sweep(const Block &b, const double *Qs, double *Ts, int sj, const double *cg, const double *dxg,
-                      const Edge1D &e, int l0, int nl, Fin fin) {
+                      const Edge1D &e, int l0, int nl, int f0, int f1, Fin fin) {
   const int st = XDIR ? 1 : sj, ls = XDIR ? sj : 1;
   const int st2 = 2 * st;
-  const int start = e.start, n = e.end - e.start + 1;
-  const int st0 = MORD < 8 ? -1 : -2, stn = MORD < 8 ? 4 : 5;
-  const int s1w = XDIR ? n + stn : nl, s1h = XDIR ? nl : n + stn;
+  const int start = e.start;
+  if (nl <= 0 || f1 < f0) return;  // uniform over the block
+  // staged values: al at faces f0-1 .. f1+1 (hord 5/6), dm of cells f0-2 .. f1+1 (hord 8)
+  const int st0 = MORD < 8 ? -1 : -2, stn = MORD < 8 ? 3 : 4;
+  const int n = f1 - f0 + 1;
+  const int s1w = XDIR ? n + stn - 1 : nl, s1h = XDIR ? nl : n + stn - 1;
   b.par2(s1w, s1h, [&](int ir, int jr) {
-    const int f = start + st0 + (XDIR ? ir : jr), l = l0 + (XDIR ? jr : ir);
+    const int f = f0 + st0 + (XDIR ? ir : jr), l = l0 + (XDIR ? jr : ir);
     const double *qp = Qs + f * st + l * ls;
     if (MORD < 8) {
       Ts[f * st + l * ls] = PPM_P1 * (qp[-st] + qp[0]) + PPM_P2 * (qp[-st2] + qp[st]);
@@ -40,16 +44,17 @@ FV_DEV void ppm_sweep(const Block &b, const double *Qs, double *Ts, int sj, cons
       const int l = l0 + t / 6, r = t % 6;
       if (r < 3 ? !e.lo : !e.hi) return;
       const int f = r < 3 ? start - 1 + r : e.end + (r - 3);
+      if (f < f0 - 1 || f > f1 + 1) return;
       auto q = [&](int ii) { return Qs[ii * st + l * ls]; };
       auto dx = [&](int ii) { return dxg[ii * st + l * ls]; };
       Ts[f * st + l * ls] = ppm_al_lt8(q, dx, f, e);
     });
   }
-  const int s2w = XDIR ? n + 1 : nl, s2h = XDIR ? nl : n + 1;
+  const int s2w = XDIR ? n : nl, s2h = XDIR ? nl : n;
   // hord 8: faces redone by S2b are skipped here, so that fin() runs exactly once per face
   const int lo_lim = (MORD >= 8 && e.lo) ? start + 2 : start - 1, hi_lim = (MORD >= 8 && e.hi) ? e.end - 1 : e.end + 2;
   b.par2(s2w, s2h, [&](int ir, int jr) {
-    const int f = start + (XDIR ? ir : jr), l = l0 + (XDIR ? jr : ir);
+    const int f = f0 + (XDIR ? ir : jr), l = l0 + (XDIR ? jr : ir);
     if (f <= lo_lim || f >= hi_lim) return;
     const int p = f * st + l * ls;
     const double c = FV_LDG(cg + p);
@@ -90,6 +95,7 @@ FV_DEV void ppm_sweep(const Block &b, const double *Qs, double *Ts, int sj, cons
       if (r < 3 ? !e.lo : !e.hi) return;
       const int f = r < 3 ? start + r : e.end - 1 + (r - 3);
       if (r >= 3 && e.lo && f <= start + 2) return;  // tiny domains: already done by the low-edge pass
+      if (f < f0 || f > f1) return;
       const int p = f * st + l * ls;
       auto q = [&](int ii) { return Qs[ii * st + l * ls]; };
       auto tt = [&](int ii) { return Ts[ii * st + l * ls]; };
