@@ -123,18 +123,29 @@ FV_DEV void delnflux_plane(const fv3_geom &g, const fv3_grid &m, int s, const fv
     const double v = q[p];
     D2[p] = copy_q ? v : dk * v;
   });
+  // cube-corner remaps (copy_corners_x / _y) only matter where a difference touches a corner halo block: rows and
+  // columns within one cell of the compute domain's ends; everywhere else the plain neighbours are read
+  const int iec = isc + nx - 1, jsc = h, jec = h + g.ny - 1;
+  const bool any_corner = (fv3::on_west(g, s) || fv3::on_east(g, s)) && (fv3::on_south(g, s) || fv3::on_north(g, s));
+  auto near_corner = [&](int i, int j) { return any_corner && (i <= isc || i > iec) && (j <= jsc || j > jec); };
   auto d2x = [&](int ii, int jj) {
-    if (hi) fv3::corner_x(g, s, ii, jj);
+    fv3::corner_x(g, s, ii, jj);
     return D2[jj * sj + ii];
   };
   auto d2y = [&](int ii, int jj) {
-    if (hi) fv3::corner_y(g, s, ii, jj);
+    fv3::corner_y(g, s, ii, jj);
     return D2[jj * sj + ii];
   };
   b.rect(isc - r, isc + nx + r + 1, ja - r, jb + r + 1, [&](int i, int j) {
     const int p = j * sj + i;
-    if (j < jb + r) FX[p] = del6_v[p] * (d2x(i - 1, j) - d2x(i, j));
-    if (i < isc + nx + r) FY[p] = del6_u[p] * (d2y(i, j - 1) - d2y(i, j));
+    if (hi && near_corner(i, j)) {
+      if (j < jb + r) FX[p] = del6_v[p] * (d2x(i - 1, j) - d2x(i, j));
+      if (i < isc + nx + r) FY[p] = del6_u[p] * (d2y(i, j - 1) - d2y(i, j));
+    } else {
+      const double d0 = D2[p];
+      if (j < jb + r) FX[p] = del6_v[p] * (D2[p - 1] - d0);
+      if (i < isc + nx + r) FY[p] = del6_u[p] * (D2[p - sj] - d0);
+    }
   });
   if (!hi) return;
   for (int n = 0; n < nmax; ++n) {
@@ -145,14 +156,14 @@ FV_DEV void delnflux_plane(const fv3_geom &g, const fv3_grid &m, int s, const fv
     });
     b.rect(isc - nt, isc + nx + nt + 1, ja - nt, jb + nt + 1, [&](int i, int j) {
       const int p = j * sj + i;
-      int ia = i - 1, jaa = j, ib = i, jbb = j;
-      fv3::corner_x(g, s, ia, jaa);
-      fv3::corner_x(g, s, ib, jbb);
-      if (j < jb + nt) FX[p] = -del6_v[p] * (D2[jaa * sj + ia] - D2[jbb * sj + ib]);
-      ia = i, jaa = j - 1, ib = i, jbb = j;
-      fv3::corner_y(g, s, ia, jaa);
-      fv3::corner_y(g, s, ib, jbb);
-      if (i < isc + nx + nt) FY[p] = -del6_u[p] * (D2[jaa * sj + ia] - D2[jbb * sj + ib]);
+      if (near_corner(i, j)) {
+        if (j < jb + nt) FX[p] = -del6_v[p] * (d2x(i - 1, j) - d2x(i, j));
+        if (i < isc + nx + nt) FY[p] = -del6_u[p] * (d2y(i, j - 1) - d2y(i, j));
+      } else {
+        const double d0 = D2[p];
+        if (j < jb + nt) FX[p] = -del6_v[p] * (D2[p - 1] - d0);
+        if (i < isc + nx + nt) FY[p] = -del6_u[p] * (D2[p - sj] - d0);
+      }
     });
   }
 }

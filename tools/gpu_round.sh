@@ -11,4 +11,9 @@ cat gpurun_out/${tag}_bench.json; tail -45 gpurun_out/${tag}_bench.err
 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled --csv \
     --log-file gpurun_out/${tag}_launches_k1n1.csv python tools/profile_step.py > gpurun_out/${tag}_launches.log 2>&1
 tail -2 gpurun_out/${tag}_launches.log
+
+# DRAM bytes per launch of the same step (profiles/traffic.json via tools/stage_traffic.py)
+timeout 900 ncu --profile-from-start off --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
+    --kernel-name-base demangled --csv --log-file gpurun_out/${tag}_dram_k1n1.csv python tools/profile_step.py > gpurun_out/${tag}_dram.log 2>&1
+tail -1 gpurun_out/${tag}_dram.log
 if [ $# -gt 0 ]; then PROFILE_ARGS="" timeout 1500 tools/ncu_kernels.sh $tag "$@"; fi
