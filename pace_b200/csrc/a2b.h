@@ -160,13 +160,29 @@ FV_DEV void a2b_plane(const fv3_geom &g, const fv3_grid &m, int s, const B &b, c
   // qx on corner columns isc..iec+1, rows ja-2..jb+1; qy on rows ja..jb, columns isc-2..iec+2
   const int xj0 = b.lo(jsc - 2, 2), xj1 = b.hi(jec + 3, 2), yj0 = ja, yj1 = jb + 1;
   const int nxc = g.nx + 1, nxw = g.nx + 4, nxr = xj1 - xj0, nyr = yj1 - yj0;
-  b.par(nxc * nxr + nxw * nyr, [&](int t) {
-    if (t < nxc * nxr) {
+  // The two columns (rows) either side of a tile edge use the one-sided formulas (divides, metric loads): they are
+  // separate, densely packed tasks of the same phase instead of a few slow lanes in every warp of the bulk pass.
+  const int nbx = nxc * nxr, nby = nxw * nyr, nex = 4 * nxr, ney = 4 * nxw;
+  b.par(nbx + nby + nex + ney, [&](int t) {
+    if (t < nbx) {
       const int jr = t / nxc, i = isc + (t - jr * nxc), j = xj0 + jr;
+      if (i <= isc + 1 || i >= iec) return;
+      QX[j * sj + i] = A2B::b2 * (q(i - 2, j) + q(i + 1, j)) + A2B::b1 * (q(i - 1, j) + q(i, j));
+    } else if (t < nbx + nby) {
+      const int t2 = t - nbx;
+      const int jr = t2 / nxw, i = isc - 2 + (t2 - jr * nxw), j = yj0 + jr;
+      if (j <= jsc + 1 || j >= jec) return;
+      QY[j * sj + i] = A2B::b2 * (q(i, j - 2) + q(i, j + 1)) + A2B::b1 * (q(i, j - 1) + q(i, j));
+    } else if (t < nbx + nby + nex) {
+      const int t2 = t - nbx - nby;
+      const int c = t2 & 3, j = xj0 + (t2 >> 2), i = c < 2 ? isc + c : iec + (c - 2);
+      if (c >= 2 && i <= isc + 1) return;  // tiny domains: column already done as a west column
       QX[j * sj + i] = a2b_qx(g, m, s, q, i, j);
     } else {
-      const int t2 = t - nxc * nxr;
-      const int jr = t2 / nxw, i = isc - 2 + (t2 - jr * nxw), j = yj0 + jr;
+      const int t2 = t - nbx - nby - nex;
+      const int c = t2 / nxw, i = isc - 2 + (t2 - c * nxw), j = c < 2 ? jsc + c : jec + (c - 2);
+      if (c >= 2 && j <= jsc + 1) return;
+      if (j < yj0 || j >= yj1) return;
       QY[j * sj + i] = a2b_qy(g, m, s, q, i, j);
     }
   });

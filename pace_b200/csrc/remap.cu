@@ -204,6 +204,10 @@ FV_DEV void map_chain(const fv3_geom &g, const MapBatch &mb, int f, int s, int i
   const double qmin = mb.qmin[f];
   auto A1 = [&](int k) { return FV_LDG(a1p + k * sk); };
   auto P1 = [&](int k) { return FV_LDG(pe1 + k * sk); };
+#ifndef FV3_HOSTSIM
+  // the whole column of layer means is read by four passes: pull it into L2 once, now
+  for (int k = 8; k < km; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(a1p + k * sk));
+#endif
   // set_initial_vals (remap_profile.py:150-250)
   if (iv != -2) {
     double p_k = P1(1), p_k1 = P1(2);
