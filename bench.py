@@ -334,9 +334,7 @@ def main():
                "steps": n_e2e, "note": "full DycoreState copied from pinned host memory before and back to it after every step_dynamics"}
 
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return
+        return finish(dist)
 
     # ---- roofline of the dominant stage -------------------------------------------------------------------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -390,8 +388,20 @@ def main():
         "launch_mode": mode, "ms_per_step_eager": ms_eager, "host_enqueue_ms_per_step": host_enqueue_ms,
     }
     print(json.dumps(line), flush=True)
+    finish(dist)
+
+
+def finish(dist):
+    """End the process once its work is done.  Multi-rank runs leave through os._exit: tearing down an NCCL process group
+    whose send/recv kernels were captured into a CUDA graph can block in the communicator's finalizer, and nothing
+    remains to be flushed but the standard streams."""
+    sys.stdout.flush()
+    sys.stderr.flush()
     if dist is not None:
-        dist.destroy_process_group()
+        import torch
+
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -5,16 +5,30 @@
 // (pace_b200/util/topology.py), so the device side is a pure indexed copy.
 #include "common.h"
 
+namespace {
+constexpr int HALO_KB = 8;
+}
+
 extern "C" {
 
 int fv3_halo_gather(const fv3_geom *geom, double *const *fields, int n_fields, int nlev, const int64_t *dst_off,
                     const int64_t *src_off, const int8_t *dst_comp, const int8_t *src_comp, const double *sign,
                     int64_t n_entries, void *stream) {
   const int64_t sk = nlev > 1 ? geom->sk : 0;
-  fv3::launch1d((cudaStream_t)stream, n_entries, nlev, n_fields, FV_LAMBDA(int64_t e, int k, int f) {
-    const double *src = fields[src_comp[e] * n_fields + f];
-    double *dst = fields[dst_comp[e] * n_fields + f];
-    dst[dst_off[e] + k * sk] = sign[e] * src[src_off[e] + k * sk];
+  // one thread moves HALO_KB levels of one table entry: the entry is decoded once and the level loads are
+  // independent requests in flight together
+  fv3::launch1d((cudaStream_t)stream, n_entries, (nlev + HALO_KB - 1) / HALO_KB, n_fields, FV_LAMBDA(int64_t e, int kb, int f) {
+    const double *src = fields[src_comp[e] * n_fields + f] + src_off[e];
+    double *dst = fields[dst_comp[e] * n_fields + f] + dst_off[e];
+    const double sg = sign[e];
+    const int k0 = kb * HALO_KB;
+    double v[HALO_KB];
+#pragma unroll
+    for (int n = 0; n < HALO_KB; ++n)
+      if (k0 + n < nlev) v[n] = src[(k0 + n) * sk];
+#pragma unroll
+    for (int n = 0; n < HALO_KB; ++n)
+      if (k0 + n < nlev) dst[(k0 + n) * sk] = sg * v[n];
   });
   return fv3::check_launch("fv3_halo_gather");
 }
