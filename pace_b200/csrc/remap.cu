@@ -11,6 +11,7 @@
 //                          674-695)
 //   fv3_fv_setup        <- fv_setup + pt_to_potential_density_pt (moist_cv.py:175-234, fv_dynamics.py:39-52)
 #include "common.h"
+#include "stream.h"
 
 namespace {
 
@@ -144,54 +145,6 @@ FV_HD void map_coef(int L, int km, int iv, double qmin, double am2, double am1, 
 }
 
 
-// k-loops over streamed global operands: body(k, a, b) for k in [kb, ke) ascending (or descending for stream_down),
-// with a(k) = la(k), b(k) = lb(k) requested DEPTH trips before their use and held in a register ring.
-constexpr int STREAM_DEPTH = 8;
-template <class LA, class LB, class B>
-FV_DEV void stream_up(int kb, int ke, LA la, LB lb, B body) {
-  double ra[STREAM_DEPTH], rb[STREAM_DEPTH];
-#pragma unroll
-  for (int n = 0; n < STREAM_DEPTH; ++n) {
-    const int k = kb + n;
-    ra[n] = k < ke ? la(k) : 0.0;
-    rb[n] = k < ke ? lb(k) : 0.0;
-  }
-  for (int k0 = kb; k0 < ke; k0 += STREAM_DEPTH) {
-#pragma unroll
-    for (int n = 0; n < STREAM_DEPTH; ++n) {
-      const int k = k0 + n;
-      if (k < ke) {
-        const double a = ra[n], b = rb[n];
-        const int kn = k + STREAM_DEPTH;
-        ra[n] = kn < ke ? la(kn) : 0.0;
-        rb[n] = kn < ke ? lb(kn) : 0.0;
-        body(k, a, b);
-      }
-    }
-  }
-}
-template <class LA, class B>
-FV_DEV void stream_down(int kb, int ke, LA la, B body) {  // k = ke-1 .. kb
-  double ra[STREAM_DEPTH];
-#pragma unroll
-  for (int n = 0; n < STREAM_DEPTH; ++n) {
-    const int k = ke - 1 - n;
-    ra[n] = k >= kb ? la(k) : 0.0;
-  }
-  for (int k0 = ke - 1; k0 >= kb; k0 -= STREAM_DEPTH) {
-#pragma unroll
-    for (int n = 0; n < STREAM_DEPTH; ++n) {
-      const int k = k0 - n;
-      if (k >= kb) {
-        const double a = ra[n];
-        const int kn = k - STREAM_DEPTH;
-        ra[n] = kn >= kb ? la(kn) : 0.0;
-        body(k, a);
-      }
-    }
-  }
-}
-
 // Inputs are read through the read-only path (FV_LDG) and streamed a few levels ahead of their use: q1 is only
 // written by this chain's final copy, after its last read.
 template <class QS, class GS>
@@ -223,7 +176,7 @@ FV_DEV void map_chain(const fv3_geom &g, const MapBatch &mb, int f, int s, int i
     }
     double d4 = 0.0;
     // trip k consumes pe1[k+2] and a1[k+1] (to set up trip k+1)
-    stream_up(1, km, [&](int k) { return k + 2 <= km ? P1(k + 2) : 0.0; }, [&](int k) { return k + 1 < km ? A1(k + 1) : 0.0; },
+    fv3::stream_up(1, km, [&](int k) { return k + 2 <= km ? P1(k + 2) : 0.0; }, [&](int k) { return k + 1 < km ? A1(k + 1) : 0.0; },
               [&](int k, double p_next, double a_next) {
                 d4 = dpm / dpk;
                 const double bet = 2.0 + d4 + d4 - gm;
@@ -246,7 +199,7 @@ FV_DEV void map_chain(const fv3_geom &g, const MapBatch &mb, int f, int s, int i
       Q(km) = (2.0 * d4 * (d4 + 1.0) * ak + am - a_bot * qm) / (d4 * (d4 + 0.5) - a_bot * gm);
     }
     double qn = Q(km);
-    stream_down(0, km, [&](int k) { return G(k); }, [&](int k, double gk) {
+    fv3::stream_down(0, km, [&](int k) { return G(k); }, [&](int k, double gk) {
       qn = Q(k) - gk * qn;
       Q(k) = qn;
     });
@@ -263,7 +216,7 @@ FV_DEV void map_chain(const fv3_geom &g, const MapBatch &mb, int f, int s, int i
     double grm = dpm / dpk;  // gr[1]
     double qm = (3.0 * (am + ak) - q0) / (2.0 + grm + grm - gm);
     Q(1) = qm;
-    stream_up(2, km, [&](int k) { return P1(k + 1); }, [&](int k) { return A1(k); }, [&](int k, double p_new, double a_new) {
+    fv3::stream_up(2, km, [&](int k) { return P1(k + 1); }, [&](int k) { return A1(k); }, [&](int k, double p_new, double a_new) {
       dpm = dpk;
       am = ak;
       p_k = p_k1;
@@ -285,7 +238,7 @@ FV_DEV void map_chain(const fv3_geom &g, const MapBatch &mb, int f, int s, int i
     });
     Q(km) = qsv;
     double qn = Q(km - 1);
-    stream_down(0, km - 1, [&](int k) { return G(k + 1); }, [&](int k, double gk1) {
+    fv3::stream_down(0, km - 1, [&](int k) { return G(k + 1); }, [&](int k, double gk1) {
       qn = Q(k) - gk1 * qn;
       Q(k) = qn;
     });
@@ -293,7 +246,7 @@ FV_DEV void map_chain(const fv3_geom &g, const MapBatch &mb, int f, int s, int i
   // apply_constraints (:253-337) on the interior interfaces
   {
     double a_m2 = 0.0, a_m1 = A1(0), a_0 = A1(1);
-    stream_up(1, km, [&](int k) { return k + 1 < km ? A1(k + 1) : 0.0; }, [&](int) { return 0.0; }, [&](int k, double a_p1, double) {
+    fv3::stream_up(1, km, [&](int k) { return k + 1 < km ? A1(k + 1) : 0.0; }, [&](int) { return 0.0; }, [&](int k, double a_p1, double) {
       const double tmp = a_m1 > a_0 ? a_m1 : a_0, tmp2 = a_m1 < a_0 ? a_m1 : a_0;
       double qk = Q(k);
       if (k == 1 || k == km - 1) {
