@@ -21,7 +21,7 @@
 namespace fv3 {
 
 constexpr int COL_TILE = 32;
-constexpr int COL_WARPS = 8;  // 256 threads: three CTAs (3 x 61 KB of column arrays) share an SM
+constexpr int COL_WARPS = 16;
 
 struct Tile {
   double *sm;       // n_arrays * nlev * COL_TILE doubles
