@@ -203,8 +203,10 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
+        # rank 0 prints ONE JSON line on stdout: NCCL's version banner / debug output goes to stderr
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+            os.environ.pop("NCCL_DEBUG", None)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device(device))
         pc = ProcessComm.from_torch_distributed()
 
