@@ -377,6 +377,30 @@ int fv3_d_sw(fv3_ctx *ctx, double *delpc, double *delp, double *pt, double *u, d
       const double ut0 = ucc[o], utm = ucc[o - sj], vt0 = vcc[o], vtm = vcc[o - 1];
       kev = dt6 * ((ut0 + utm) * ((io1 + 1) * u0 - (io1 * um)) + (vt0 + vtm) * ((jo1 + 1) * v0 - (jo1 * vm)) +
                    (((jo1 + 1) * ut0 - (jo1 * utm)) + vsign * ((io1 + 1) * vt0 - (io1 * vtm))) * ((io2 + 1) * u0 - (io2 * um)));
+    } else if (!((W && i <= isc + 3) || (E && i >= iec - 2) || (S && j <= jsc + 3) || (N && j >= jec - 2))) {
+      // away from the tile edges: interior edge values, no zeroed parabolas (same expressions as advect_along)
+      auto adv = [&](const double *q, int64_t st, double ubv, double cfl) {
+        const double qm2 = q[-2 * st], ql = q[-st], qr = q[0], qp1 = q[st];
+        const double al0 = fv3::PPM_P1 * (qm2 + ql) + fv3::PPM_P2 * (q[-3 * st] + qr);
+        const double al1 = fv3::PPM_P1 * (ql + qr) + fv3::PPM_P2 * (qm2 + qp1);
+        const double al2 = fv3::PPM_P1 * (qr + qp1) + fv3::PPM_P2 * (ql + q[2 * st]);
+        const double bl_l = al0 - ql, br_l = al1 - ql, bl_r = al1 - qr, br_r = al2 - qr;
+        const double b0_l = bl_l + br_l, b0_r = bl_r + br_r;
+        const double fx0 = fv3::ppm_fx1(cfl, br_l, b0_l, bl_r, b0_r);
+        bool s_l, s_r;
+        if (mord == 5) {
+          s_l = bl_l * br_l < 0;
+          s_r = bl_r * br_r < 0;
+        } else {
+          s_l = (3.0 * fabs(b0_l)) < fabs(bl_l - br_l);
+          s_r = (3.0 * fabs(b0_r)) < fabs(bl_r - br_r);
+        }
+        const double mask = (s_l || s_r) ? 1.0 : 0.0;
+        return ubv > 0.0 ? ql + fx0 * mask : qr + fx0 * mask;
+      };
+      const double cflx = ub > 0 ? ub * dt * m.rdx[o2 - 1] : ub * dt * m.rdx[o2];
+      const double cfly = vb > 0 ? vb * dt * m.rdy[o2 - sj] : vb * dt * m.rdy[o2];
+      kev = 0.5 * dt * (ub * adv(u + o, 1, ub, cflx) + vb * adv(v + o, sj, vb, cfly));
     } else {
       const fv3::Edge1D ex{W, E, isc, iec}, ey{S, N, jsc, jec};
       auto qu = [&](int ii) { return u[O3(s, ii, j, k)]; };

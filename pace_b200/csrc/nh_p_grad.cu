@@ -162,6 +162,17 @@ int fv3_del2cubed(fv3_ctx *ctx, double *qdel, double cd, int nmax, int nk, void 
       };
       auto fx = [&](int ii, int jj) { return m.del6_v[O2(s, ii, jj)] * (qx(ii - 1, jj) - qx(ii, jj)); };
       auto fy = [&](int ii, int jj) { return m.del6_u[O2(s, ii, jj)] * (qy(ii, jj - 1) - qy(ii, jj)); };
+      // away from the cube corners (two cells either way) no corner fill or corner copy is read: plain neighbours
+      const bool near_corner = (W || E) && (S || N) && (i <= isc + 1 || i >= iec - 1) && (j <= jsc + 1 || j >= jec - 1);
+      if (!near_corner) {
+        const int64_t o = O3(s, i, j, k), o2 = O2(s, i, j);
+        const int sj = g.sj;
+        const double qc = qo[o];
+        const double fx0 = m.del6_v[o2] * (qo[o - 1] - qc), fx1 = m.del6_v[o2 + 1] * (qc - qo[o + 1]);
+        const double fy0 = m.del6_u[o2] * (qo[o - sj] - qc), fy1 = m.del6_u[o2 + sj] * (qc - qo[o + sj]);
+        qn[o] = qc + cd * m.rarea[o2] * (fx0 - fx1 + fy0 - fy1);
+        return;
+      }
       // the copy `qdel = q` keeps the y-corner-copied field (the last in-place copy) outside the compute domain
       const double base = qy(i, j);
       qn[O3(s, i, j, k)] = base + cd * m.rarea[O2(s, i, j)] * (fx(i, j) - fx(i + 1, j) + fy(i, j) - fy(i, j + 1));
