@@ -78,6 +78,17 @@ void divg_iteration(const fv3_ctx *ctx, cudaStream_t st, const double *dold, dou
   const int isc = x.isc, iec = x.iec, jsc = x.jsc, jec = x.jec;
   fv3::launch3d(ctx, st, isc - nt, iec + nt + 2, jsc - nt, jec + nt + 2, k0, g.nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     const bool W = fv3::on_west(g, s), E = fv3::on_east(g, s), S = fv3::on_south(g, s), N = fv3::on_north(g, s);
+    // away from the cube corners (three points either way) no corner fill is read and no corner term applies:
+    // the plain five-point form
+    if (!((W || E) && (S || N) && (i <= isc + 2 || i >= iec - 1) && (j <= jsc + 2 || j >= jec - 1))) {
+      const int64_t o = O3(s, i, j, k), o2 = O2(s, i, j);
+      const int sj = g.sj;
+      const double dc = dold[o];
+      const double ucm = (dc - dold[o - sj]) * m.divg_v[o2 - sj], uc0 = (dold[o + sj] - dc) * m.divg_v[o2];
+      const double vcm = (dc - dold[o - 1]) * m.divg_u[o2 - 1], vc0 = (dold[o + 1] - dc) * m.divg_u[o2];
+      dnew[o] = (ucm - uc0 + vcm - vc0) * m.rarea_c[o2];
+      return;
+    }
     auto dgx = [&](int ii, int jj) {
       if (fillc) bgrid_corner_x(g, s, ii, jj);
       return dold[O3(s, ii, jj, k)];
