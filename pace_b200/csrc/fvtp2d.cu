@@ -104,6 +104,11 @@ FV_DEV void fvtp2d_plane(const fv3_geom &g, const fv3_grid &m, int s, int k, con
                               [&](int p, double val) { A[p] = 0.5 * (val + A[p]) * FV_LDG(yu + p); });
 }
 
+#ifndef FV3_HOSTSIM
+__device__ __forceinline__ bool delnflux_plane_fast(const fv3_geom &g, const fv3_grid &m, int s, const fv3::Block &b,
+                                                    const double *q, double dk, bool hi, int nmax, bool copy_q,
+                                                    double *D2, double *FX, double *FY);
+#endif
 // ---- plane-resident del-n fluxes (DelnFlux / DelnFluxNoSG, delnflux.py:59-238,1164-1261) ------------------------
 // D2: the field being differenced (damp * q, then the Laplacians of the previous fluxes), FX / FY: its fluxes.
 // All nord iterations run in shared memory; on return FX / FY hold fx2 / fy2 on the strip's part of the interface
@@ -111,6 +116,9 @@ FV_DEV void fvtp2d_plane(const fv3_geom &g, const fv3_grid &m, int s, int k, con
 // whose results reach nt cells beyond the compute domain is evaluated nt rows beyond the strip.
 FV_DEV void delnflux_plane(const fv3_geom &g, const fv3_grid &m, int s, const fv3::Block &b, const double *q, double dk,
                           bool hi, int nmax, bool copy_q, double *D2, double *FX, double *FY) {
+#ifndef FV3_HOSTSIM
+  if (delnflux_plane_fast(g, m, s, b, q, dk, hi, nmax, copy_q, D2, FX, FY)) return;
+#endif
   const int sj = g.sj, h = g.halo, nx = g.nx;
   const int isc = h;
   const int ja = b.ja, jb = b.jb;
@@ -167,6 +175,115 @@ FV_DEV void delnflux_plane(const fv3_geom &g, const fv3_grid &m, int s, const fv
     });
   }
 }
+
+#ifndef FV3_HOSTSIM
+// Same phases with a FIXED thread -> point assignment over the largest phase domain (3 cells / rows beyond the strip's
+// compute part): the per-point flux coefficients (del6_v, del6_u) and the corner flags are fetched ONCE into
+// registers, so the flux phases run on shared memory and registers only — no global-load wait at their start.  Same expressions as delnflux_plane; returns false when a thread would own more than DN_SLOTS
+// points (the caller then uses the generic form).
+constexpr int DN_SLOTS = 6;
+__device__ __forceinline__ bool delnflux_plane_fast(const fv3_geom &g, const fv3_grid &m, int s, const fv3::Block &b,
+                                                    const double *q, double dk, bool hi, int nmax, bool copy_q,
+                                                    double *D2, double *FX, double *FY) {
+  const int sj = g.sj, h = g.halo, nx = g.nx;
+  const int isc = h, iec = isc + nx - 1, jsc = h, jec = h + g.ny - 1;
+  const int ja = b.ja, jb = b.jb;
+  const int w = nx + 6, npts = w * (jb - ja + 6), nthr = (int)blockDim.x;
+  if (npts > DN_SLOTS * nthr) return false;
+  const int64_t o2b = O2(s, 0, 0);
+  const double *del6_u = m.del6_u + o2b, *del6_v = m.del6_v + o2b, *rarea = m.rarea + o2b;
+  const bool any_corner = (fv3::on_west(g, s) || fv3::on_east(g, s)) && (fv3::on_south(g, s) || fv3::on_north(g, s));
+  double dv[DN_SLOTS], du[DN_SLOTS];
+  unsigned nc = 0;
+  const float inv = 1.0f / (float)w;
+  // slot n of this thread: point t = tid + n * nthr of the rectangle (i = -1000 for an empty slot: every domain test
+  // fails); recomputed where needed instead of held in registers
+  auto J = [&](int n) {
+    const int t = (int)threadIdx.x + n * nthr;
+    return (int)(((float)t + 0.5f) * inv);
+  };
+  auto I = [&](int n, int jr) {
+    const int t = (int)threadIdx.x + n * nthr;
+    return t < npts ? isc - 3 + (t - jr * w) : -1000;
+  };
+#pragma unroll
+  for (int n = 0; n < DN_SLOTS; ++n) {
+    const int jr = J(n), i = I(n, jr), j = ja - 3 + jr;
+    dv[n] = du[n] = 0.0;
+    if (i > -1000) {
+      const int p = j * sj + i;
+      dv[n] = FV_LDG(del6_v + p);
+      du[n] = FV_LDG(del6_u + p);
+      if (any_corner && (i <= isc || i > iec) && (j <= jsc || j > jec)) nc |= 1u << n;
+    }
+  }
+  auto d2x = [&](int ii, int jj) {
+    fv3::corner_x(g, s, ii, jj);
+    return D2[jj * sj + ii];
+  };
+  auto d2y = [&](int ii, int jj) {
+    fv3::corner_y(g, s, ii, jj);
+    return D2[jj * sj + ii];
+  };
+  const int r = hi ? nmax : 0;
+#pragma unroll
+  for (int n = 0; n < DN_SLOTS; ++n) {
+    const int jr = J(n), i = I(n, jr), j = ja - 3 + jr;
+    if (i >= isc - r - 1 && i < isc + nx + r + 1 && j >= ja - r - 1 && j < jb + r + 1) {
+      const int p = j * sj + i;
+      const double v = q[p];
+      D2[p] = copy_q ? v : dk * v;
+    }
+  }
+  __syncthreads();
+  // one flux phase: sign = +1 for the first differences, -1 for the iterations (written as in the generic form)
+  auto flux = [&](int e, bool first) {
+#pragma unroll
+    for (int n = 0; n < DN_SLOTS; ++n) {
+      const int jr = J(n), i = I(n, jr), j = ja - 3 + jr;
+      if (i >= isc - e && i < isc + nx + e + 1 && j >= ja - e && j < jb + e + 1) {
+        const int p = j * sj + i;
+        const bool fxo = j < jb + e, fyo = i < isc + nx + e;
+        if ((first ? hi : true) && ((nc >> n) & 1u)) {
+          if (first) {
+            if (fxo) FX[p] = dv[n] * (d2x(i - 1, j) - d2x(i, j));
+            if (fyo) FY[p] = du[n] * (d2y(i, j - 1) - d2y(i, j));
+          } else {
+            if (fxo) FX[p] = -dv[n] * (d2x(i - 1, j) - d2x(i, j));
+            if (fyo) FY[p] = -du[n] * (d2y(i, j - 1) - d2y(i, j));
+          }
+        } else {
+          const double d0 = D2[p];
+          if (first) {
+            if (fxo) FX[p] = dv[n] * (D2[p - 1] - d0);
+            if (fyo) FY[p] = du[n] * (D2[p - sj] - d0);
+          } else {
+            if (fxo) FX[p] = -dv[n] * (D2[p - 1] - d0);
+            if (fyo) FY[p] = -du[n] * (D2[p - sj] - d0);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  };
+  flux(r, true);
+  if (!hi) return true;
+  for (int it = 0; it < nmax; ++it) {
+    const int nt = nmax - 1 - it;
+#pragma unroll
+    for (int n = 0; n < DN_SLOTS; ++n) {
+      const int jr = J(n), i = I(n, jr), j = ja - 3 + jr;
+      if (i >= isc - nt - 1 && i < isc + nx + nt + 1 && j >= ja - nt - 1 && j < jb + nt + 1) {
+        const int p = j * sj + i;
+        D2[p] = (FX[p] - FX[p + 1] + FY[p] - FY[p + sj]) * FV_LDG(rarea + p);
+      }
+    }
+    __syncthreads();
+    flux(nt, false);
+  }
+  return true;
+}
+#endif
 
 // mode: 0 = transport fluxes only; 1 = fx += fx2 (DelnFlux without mass); 2 = fx += 0.5*damp*(mass[-1]+mass)*fx2
 template <int MORD>
