@@ -217,6 +217,7 @@ void divergence_damping(fv3_ctx *ctx, cudaStream_t st, const double *u, const do
     double *SQ = b.plane(0), *QX = b.plane(1), *QY = b.plane(2), *OUT = b.plane(3);
     const int64_t ob = O3(s, 0, 0, k);
     const bool smag = !(dddmp < 1e-5);
+    if (smag) b.prefetch_next_wave(vort_a, g, k);
     if (smag) fv3::a2b_plane(g, m, s, b, vort_a + ob, SQ, QX, QY, OUT);
     const int sj2 = g.sj, h2 = g.halo;
     const double *rarea_unused = nullptr;

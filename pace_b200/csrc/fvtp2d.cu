@@ -53,6 +53,7 @@ FV_DEV void fvtp2d_plane(const fv3_geom &g, const fv3_grid &m, int s, int k, con
   const int nwi = ied + 1, nwj = jed + 1;
   // this strip: fluxes on cell rows [ja, jb) and y faces [ja, jb]; q, fx_in and q_j on rows [rl, rh)
   const int ja = b.ja, jb = b.jb, rl = b.lo(0, h), rh = b.hi(nwj, h);
+  b.prefetch_next_wave(a.q, g, k);
   {  // operands of the later phases: start their HBM -> L2 transfer now
     b.prefetch_rows(cry, sj);
     b.prefetch_rows(crx, sj);
@@ -338,6 +339,7 @@ int fv3_delnflux_nosg(fv3_ctx *ctx, const double *q, double *fx2, double *fy2, c
   int rc = fv3::launch_planes(ctx, (cudaStream_t)stream, 0, nk, 3, FV_LAMBDA(int s, int k, const fv3::Block &b) { FV_DEV_GM
     double *D2 = b.plane(0), *FX = b.plane(1), *FY = b.plane(2);
     const int64_t ob = O3(s, 0, 0, k);
+    b.prefetch_next_wave(q, g, k);
     delnflux_plane(g, m, s, b, q + ob, damp_col[k], nord_col[k] > 0, nmax, false, D2, FX, FY);
     const int sj = g.sj, h = g.halo, nx = g.nx;
     b.rect(h, h + nx + 1, b.ja, b.jtop() + 1, [&](int i, int j) {
@@ -410,6 +412,7 @@ int fv3_tracer_subcycle(fv3_ctx *ctx, double *const *tracers, int nq, double *dp
     const int64_t ob = O3(s, 0, 0, k), o2b = O2(s, 0, 0);
     const double *rarea = m.rarea + o2b;
     b.prefetch_rows(dp1 + ob, sj);
+    b.prefetch_next_wave(tracers[0], g, k);
     for (int n = 0; n < nq; ++n) {
       double *q = tracers[n];
       if (n + 1 < nq) b.prefetch_rows(tracers[n + 1] + ob, sj);

@@ -35,6 +35,7 @@ int fv3_nh_p_grad(fv3_ctx *ctx, double *u, double *v, double *pp, double *gz, do
     auto fill = [&](double *dst, double value) {
       b.rect(h2, h2 + g.nx + 1, b.ja, b.jtop() + 1, [&](int i, int j) { dst[ob + j * sj2 + i] = value; });
     };
+    b.prefetch_next_wave(gz, g, k);
     if (k >= 1) {
       b.prefetch_rows(pp + ob, sj2);
       b.prefetch_rows(pk3 + ob, sj2);

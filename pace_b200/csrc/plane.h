@@ -30,6 +30,7 @@ struct Block {
   int ja, jb;   // owned rows: results on cell rows [ja, jb), y-faces / corner rows [ja, jb]
   int r0, r1;   // resident rows [r0, r1)
   bool last;    // jb is the top of the compute domain (this strip also stores face / corner row jb)
+  int s_next, r0_next, nrows_next;  // the (subdomain, strip rows) a CTA of the NEXT wave will start on; s_next < 0: none
 
   FV_HD double *plane(int n) const { return sm + (int64_t)n * pl - off; }
   FV_HD int jtop() const { return last ? jb : jb - 1; }  // last face / corner row this strip stores
@@ -79,6 +80,11 @@ struct Block {
   }
   // resident rows of the global plane starting at `plane0`
   FV_DEV void prefetch_rows(const double *plane0, int sj) const { prefetch_l2(plane0 + r0 * sj, (r1 - r0) * sj); }
+  // First-touch operand of a CTA one wave ahead (same level, `field` = start of the 3-D field): its HBM -> L2 transfer
+  // starts now, so that CTA's opening load phase finds it in L2.  DRAM is < 15 % busy in these kernels.
+  FV_DEV void prefetch_next_wave(const double *field, const fv3_geom &g, int k) const {
+    if (s_next >= 0) prefetch_l2(field + (int64_t)s_next * g.ss + (int64_t)k * g.sk + (int64_t)r0_next * g.sj, nrows_next * g.sj);
+  }
 };
 
 struct StripGeom {
@@ -105,8 +111,18 @@ inline StripGeom strip_geometry(const fv3_geom &g, int n_planes) {
   return sg;
 }
 
+FV_HD void strip_rows(const fv3_geom &g, int strip, int rows_per_strip, int &ja, int &jb, int &r0, int &r1) {
+  const int jend = g.halo + g.ny;
+  ja = g.halo + strip * rows_per_strip;
+  jb = ja + rows_per_strip < jend ? ja + rows_per_strip : jend;
+  r0 = ja - g.halo;
+  r1 = jb + g.halo + 1 < g.nj ? jb + g.halo + 1 : g.nj;
+}
+
 FV_HD Block make_block(const fv3_geom &g, double *sm, int strip, int rows_per_strip, int res_rows) {
   Block b;
+  b.s_next = -1;
+  b.r0_next = b.nrows_next = 0;
   b.sm = sm;
   const int jsc = g.halo, jend = g.halo + g.ny;
   b.ja = jsc + strip * rows_per_strip;
@@ -121,9 +137,23 @@ FV_HD Block make_block(const fv3_geom &g, double *sm, int strip, int rows_per_st
 
 #ifndef FV3_HOSTSIM
 template <class F>
-__global__ void __launch_bounds__(PLANE_THREADS, 2) kplane(F f, int k0, int rows_per_strip, int res_rows) {
+__global__ void __launch_bounds__(PLANE_THREADS, 2) kplane(F f, int k0, int rows_per_strip, int res_rows, int ahead) {
   extern __shared__ double plane_smem[];
-  const Block b = make_block(c_g, plane_smem, (int)blockIdx.z, rows_per_strip, res_rows);
+  Block b = make_block(c_g, plane_smem, (int)blockIdx.z, rows_per_strip, res_rows);
+  {  // blocks are dispatched level-fastest, then subdomain, then strip: `ahead` subdomains later = one wave later
+    int sn = (int)blockIdx.y + ahead, zn = (int)blockIdx.z;
+    if (sn >= (int)gridDim.y) {
+      sn -= (int)gridDim.y;
+      ++zn;
+    }
+    if (zn < (int)gridDim.z && sn < (int)gridDim.y) {
+      int ja, jb, r0, r1;
+      strip_rows(c_g, zn, rows_per_strip, ja, jb, r0, r1);
+      b.s_next = sn;
+      b.r0_next = r0;
+      b.nrows_next = r1 - r0;
+    }
+  }
   f((int)blockIdx.y, k0 + (int)blockIdx.x, b);
 }
 #endif
@@ -169,7 +199,15 @@ inline int launch_planes(const fv3_ctx *ctx, cudaStream_t st, int k0, int k1, in
     }
     configured = bytes;
   }
-  kplane<<<dim3(k1 - k0, ctx->g.n_sub, sg.ns), PLANE_THREADS, bytes, st>>>(f, k0, sg.rows_per_strip, sg.res_rows);
+  static int resident = 0;  // CTAs of this kernel resident on the device at once (2 per SM)
+  if (resident == 0) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    resident = 2 * sms;
+  }
+  const int ahead = (resident + (k1 - k0) - 1) / (k1 - k0);
+  kplane<<<dim3(k1 - k0, ctx->g.n_sub, sg.ns), PLANE_THREADS, bytes, st>>>(f, k0, sg.rows_per_strip, sg.res_rows, ahead);
   ++g_launches;
   return 0;
 #endif
