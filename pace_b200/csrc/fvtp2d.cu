@@ -82,27 +82,16 @@ FV_DEV void fvtp2d_plane(const fv3_geom &g, const fv3_grid &m, int s, int k, con
   // 4. inner x sweep on q: resident rows, faces isc .. iec+1
   fv3::ppm_sweep<MORD, true>(b, Q, T, sj, crx, dxa, ex, rl, rh - rl, isc, iec + 1, [&](int p, double val) { B[p] = val; });
   // 5. transverse updates: q_i (into Q, owned rows) and q_j (into D, compute columns of the resident rows)
-  b.template par2_pre<5>(nwi, rh - rl, [&](int i, int jr, double *v) {
-    const int j = rl + jr, p = j * sj + i;
-    v[0] = FV_LDG(area + p);
+  b.rect(0, nwi, rl, rh, [&](int i, int j) {
+    const int p = j * sj + i;
+    const double qv = Q[p], ar = FV_LDG(area + p);
     if (j >= ja && j < jb) {
-      v[1] = FV_LDG(yfx + p);
-      v[2] = FV_LDG(yfx + p + sj);
-    }
-    if (i >= isc && i <= iec) {
-      v[3] = FV_LDG(xfx + p);
-      v[4] = FV_LDG(xfx + p + 1);
-    }
-  }, [&](int i, int jr, const double *v) {
-    const int j = rl + jr, p = j * sj + i;
-    const double qv = Q[p], ar = v[0];
-    if (j >= ja && j < jb) {
-      const double y0 = v[1], y1 = v[2];
+      const double y0 = FV_LDG(yfx + p), y1 = FV_LDG(yfx + p + sj);
       const double f0 = y0 * A[p], f1 = y1 * A[p + sj];
       Q[p] = (qv * ar + f0 - f1) / (ar + y0 - y1);
     }
     if (i >= isc && i <= iec) {
-      const double x0 = v[3], x1 = v[4];
+      const double x0 = FV_LDG(xfx + p), x1 = FV_LDG(xfx + p + 1);
       const double f0 = x0 * B[p], f1 = x1 * B[p + 1];
       D[p] = (qv * ar + f0 - f1) / (ar + x0 - x1);
     }

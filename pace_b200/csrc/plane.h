@@ -48,17 +48,6 @@ struct Block {
     for (int jr = 0; jr < nrows; ++jr)
       for (int ir = 0; ir < w; ++ir) f(ir, jr);
   }
-  // as par2, with the global-memory operands of a point fetched by load(ir, jr, v) into NV registers before
-  // comp(ir, jr, v) runs
-  template <int NV, class L, class C>
-  void par2_pre(int w, int nrows, L load, C comp) const {
-    for (int jr = 0; jr < nrows; ++jr)
-      for (int ir = 0; ir < w; ++ir) {
-        double v[NV];
-        load(ir, jr, v);
-        comp(ir, jr, v);
-      }
-  }
 #else
   // One bulk L2 prefetch (cp.async.bulk.prefetch.L2) of n contiguous doubles — the resident rows of a field are
   // contiguous in HBM — issued by one thread: operands of later phases are pulled into L2 while the CTA computes.
@@ -80,25 +69,6 @@ struct Block {
     for (int t = threadIdx.x; t < n; t += blockDim.x) {
       const int jr = (int)(((float)t + 0.5f) * inv);
       f(t - jr * w, jr);
-    }
-    __syncthreads();
-  }
-  // Software-pipelined form: a thread first issues the global loads (read-only path) of TWO of its points, then
-  // computes them, so the second point's L2 latency is covered by the first point's arithmetic.
-  template <int NV, class L, class C>
-  __device__ __forceinline__ void par2_pre(int w, int nrows, L load, C comp) const {
-    const int n = w * nrows, nt = blockDim.x;
-    const float inv = 1.0f / (float)w;
-    for (int t0 = threadIdx.x; t0 < n; t0 += 2 * nt) {
-      const int t1 = t0 + nt;
-      const bool h1 = t1 < n;
-      const int j0 = (int)(((float)t0 + 0.5f) * inv), i0 = t0 - j0 * w;
-      const int j1 = h1 ? (int)(((float)t1 + 0.5f) * inv) : j0, i1 = h1 ? t1 - j1 * w : i0;
-      double v0[NV], v1[NV];
-      load(i0, j0, v0);
-      load(i1, j1, v1);
-      comp(i0, j0, v0);
-      if (h1) comp(i1, j1, v1);
     }
     __syncthreads();
   }

@@ -53,14 +53,11 @@ FV_DEV void ppm_sweep(const Block &b, const double *Qs, double *Ts, int sj, cons
   const int s2w = XDIR ? n : nl, s2h = XDIR ? nl : n;
   // hord 8: faces redone by S2b are skipped here, so that fin() runs exactly once per face
   const int lo_lim = (MORD >= 8 && e.lo) ? start + 2 : start - 1, hi_lim = (MORD >= 8 && e.hi) ? e.end - 1 : e.end + 2;
-  b.template par2_pre<1>(s2w, s2h, [&](int ir, int jr, double *v) {
-    const int f = f0 + (XDIR ? ir : jr), l = l0 + (XDIR ? jr : ir);
-    v[0] = FV_LDG(cg + f * st + l * ls);
-  }, [&](int ir, int jr, const double *v) {
+  b.par2(s2w, s2h, [&](int ir, int jr) {
     const int f = f0 + (XDIR ? ir : jr), l = l0 + (XDIR ? jr : ir);
     if (f <= lo_lim || f >= hi_lim) return;
     const int p = f * st + l * ls;
-    const double c = v[0];
+    const double c = FV_LDG(cg + p);
     const double *qp = Qs + p, *tp = Ts + p;
     if (MORD < 8) {
       const double al0 = tp[-st], al1 = tp[0], al2 = tp[st];
