@@ -81,14 +81,13 @@ int fv3_c_sw(fv3_ctx *ctx, double *delp, double *pt, const double *u, const doub
     }
     utmp[o] = ut_;
     vtmp[o] = vt_;
-  });
-
-  // K2: contravariant A-grid winds on compute + 2 (d2a2c_vect.py:68-78)
-  fv3::launch3d(ctx, st, isc - 2, iec + 3, jsc - 2, jec + 3, 0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
-    const int64_t o = O3(s, i, j, k), o2 = O2(s, i, j);
-    const double a = utmp[o], b = vtmp[o], cs = m.cosa_s[o2], r2 = m.rsin2[o2];
-    ua[o] = contravariant(a, b, cs, r2);
-    va[o] = contravariant(b, a, cs, r2);
+    // contravariant A-grid winds on compute + 2 (d2a2c_vect.py:68-78), from the values just formed
+    if (i >= isc - 2 && i <= iec + 2 && j >= jsc - 2 && j <= jec + 2) {
+      const int64_t o2 = O2(s, i, j);
+      const double cs = m.cosa_s[o2], r2 = m.rsin2[o2];
+      ua[o] = contravariant(ut_, vt_, cs, r2);
+      va[o] = contravariant(vt_, ut_, cs, r2);
+    }
   });
 
   // K2b: corner fills of utmp (3 cells), ua (2 cells) in x and vtmp, va in y (d2a2c_vect.py:81-88,157-164);
