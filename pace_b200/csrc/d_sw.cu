@@ -189,16 +189,18 @@ void divergence_damping(fv3_ctx *ctx, cudaStream_t st, const double *u, const do
     const int64_t o = O3(s, i, j, k);
     delpc[o] = divg_d[o];
   });
-  double *tmp = fv3::scratch_field(ctx, 7);
-  double *bufs[2] = {divg_d, tmp};
-  int cur = 0;
+  // the iterations go divg_d -> scratch -> scratch' -> ... and the LAST one writes its (compute-domain) result
+  // straight back into divg_d; a single iteration cannot work in place and takes the copy
+  double *tmp = fv3::scratch_field(ctx, 7), *tmp2 = fv3::scratch_field(ctx, 8);
+  const double *src = divg_d;
   for (int n = 0; n < nord; ++n) {
     const int nt = nord - (n + 1);
     const bool fillc = (n + 1 != nord);
-    divg_iteration(ctx, st, bufs[cur], bufs[1 - cur], nt, fillc, k0);
-    cur = 1 - cur;
+    double *dst = (n + 1 == nord && nord >= 2) ? divg_d : ((n & 1) ? tmp2 : tmp);
+    divg_iteration(ctx, st, src, dst, nt, fillc, k0);
+    src = dst;
   }
-  if (cur == 1) {  // result sits in the scratch buffer: bring it back over the final (compute) domain
+  if (nord == 1) {
     fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, k0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
       const int64_t o = O3(s, i, j, k);
       divg_d[o] = tmp[o];

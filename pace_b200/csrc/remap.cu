@@ -505,36 +505,41 @@ int fv3_remap_prep(fv3_ctx *ctx, double *const *tracers6, double *q_con, double 
   const fv3_geom g = ctx->g;
   const fv3_grid m = ctx->m;
   const int h = g.halo, km = g.nz;
-  fv3::launch2d(ctx, (cudaStream_t)stream, h, h + g.nx, h, h + g.ny + 1, FV_LAMBDA(int s, int i, int j) { FV_DEV_GM
-    const int64_t c0 = O3(s, i, j, 0), sk = g.sk;
+  // every statement is local to a level once the surface pressure pe[km] of the column is known: one thread per
+  // cell (the reference's k-loops carry no dependence here)
+  fv3::launch3d(ctx, (cudaStream_t)stream, h, h + g.nx, h, h + g.ny + 1, 0, km + 1, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
+    const int64_t c0 = O3(s, i, j, 0), sk = g.sk, o = c0 + k * sk;
     // init_pe on the (nx, ny+1) domain
-    for (int k = 0; k <= km; ++k) pe1[c0 + k * sk] = pe[c0 + k * sk];
-    pe2[c0] = ptop;
-    pe2[c0 + km * sk] = pe[c0 + km * sk];
+    const double pek = pe[o];
+    pe1[o] = pek;
+    if (k == 0) pe2[o] = ptop;
+    if (k == km) pe2[o] = pek;
     if (j >= h + g.ny) return;
     const double psv = pe[c0 + km * sk];
-    ps[O2(s, i, j)] = psv;
-    for (int k = 0; k < km; ++k) {
-      const int64_t o = c0 + k * sk;
+    if (k == km) {
+      ps[O2(s, i, j)] = psv;
+      pn2[o] = peln[o];
+      return;
+    }
+    {
       double cvm, gz;
       moist_cv(tracers6[0][o], tracers6[1][o], tracers6[2][o], tracers6[3][o], tracers6[4][o], tracers6[5][o], cvm, gz);
       q_con[o] = gz;
       const double cp = RDGAS / (RDGAS + cvm / (1.0 + r_vir * tracers6[0][o]));
       cappa[o] = cp;
-      pt[o] = pt[o] * exp(cp / (1.0 - cp) * log(RDG * delp[o] / delz[o] * pt[o]));
-      delz[o] = -delz[o] / delp[o];
+      const double dp_old = delp[o], dz_old = delz[o], pt_old = pt[o];
+      pt[o] = pt_old * exp(cp / (1.0 - cp) * log(RDG * dp_old / dz_old * pt_old));
+      delz[o] = -dz_old / dp_old;
     }
-    for (int k = 1; k < km; ++k) pe2[c0 + k * sk] = m.ak[k] + m.bk[k] * psv;
-    pn2[c0 + km * sk] = peln[c0 + km * sk];
-    for (int k = 0; k < km; ++k) {
-      const int64_t o = c0 + k * sk;
-      const double d = pe2[o + sk] - pe2[o];
-      dp2[o] = d;
-      delp[o] = d;
-      const double l = log(pe2[o]);
-      pn2[o] = l;
-      pk[o] = exp(akap * l);
-    }
+    const double p2k = k == 0 ? ptop : m.ak[k] + m.bk[k] * psv;
+    const double p2n = k + 1 == km ? psv : m.ak[k + 1] + m.bk[k + 1] * psv;
+    if (k >= 1) pe2[o] = p2k;
+    const double d = p2n - p2k;
+    dp2[o] = d;
+    delp[o] = d;
+    const double l = log(p2k);
+    pn2[o] = l;
+    pk[o] = exp(akap * l);
   });
   return fv3::check_launch("fv3_remap_prep");
 }
