@@ -67,13 +67,11 @@ int fv3_update_dz_d(fv3_ctx *ctx, const double *surface_height, double *height, 
     const int64_t c0 = O3(s, i, j, 0), sk = g.sk;
     const double ar = m.area[O2(s, i, j)];
     double below = 0.0;
-    // the flux operands are read-only here (read-only path: free to be fetched ahead of the height stores)
-#pragma unroll 4
     for (int k = nz; k >= 0; --k) {
       const int64_t o = c0 + k * sk;
-      const double area_after = ((ar + FV_LDG(xfx_i + o) - FV_LDG(xfx_i + o + 1)) + (ar + FV_LDG(yfx_i + o) - FV_LDG(yfx_i + o + sj))) - ar;
-      double hv = (height[o] * ar + FV_LDG(fx + o) - FV_LDG(fx + o + 1) + FV_LDG(fy + o) - FV_LDG(fy + o + sj)) / area_after +
-                  (FV_LDG(gx + o) - FV_LDG(gx + o + 1) + FV_LDG(gy + o) - FV_LDG(gy + o + sj)) / ar;
+      const double area_after = ((ar + xfx_i[o] - xfx_i[o + 1]) + (ar + yfx_i[o] - yfx_i[o + sj])) - ar;
+      double hv = (height[o] * ar + fx[o] - fx[o + 1] + fy[o] - fy[o + sj]) / area_after +
+                  (gx[o] - gx[o + 1] + gy[o] - gy[o + sj]) / ar;
       if (k == nz) {
         ws[O2(s, i, j)] = (surface_height[O2(s, i, j)] - hv) / dt;
       } else {
