@@ -218,6 +218,10 @@ int fv3_remap_finish(fv3_ctx *ctx, double *const *tracers6, const double *pe2, d
 /* ---- DynamicalCore.compute_preamble (fv_dynamics.py:440-483): fv_setup + pt_to_potential_density_pt */
 int fv3_fv_setup(fv3_ctx *ctx, double *const *tracers6, double *q_con, double *cvm, double *pkz, double *pt,
                  double *cappa, const double *delp, const double *delz, double *dp1, void *stream);
+/* ---- AdjustNegativeTracerMixingRatio.__call__ (neg_adj3.py:377-420): fix_neg_water, fillq(qgraupel), fillq(qrain),
+ * fix_water_vapor_down, fix_neg_cloud on the compute domain, in place (non-hydrostatic constants) */
+int fv3_neg_adj3(fv3_ctx *ctx, double *qvapor, double *qliquid, double *qrain, double *qsnow, double *qice,
+                 double *qgraupel, double *qcld, double *pt, const double *delp, void *stream);
 /* ---- omega_from_w (fv_dynamics.py:55-64) */
 int fv3_omega_from_w(fv3_ctx *ctx, const double *delp, const double *delz, const double *w, double *omga, void *stream);
 

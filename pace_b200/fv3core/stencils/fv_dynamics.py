@@ -12,6 +12,7 @@ from ...util.timer import NullTimer
 from ..dycore_state import TRACER_VARIABLES, DycoreState
 from . import acoustic_misc, fvtp2d
 from .dyn_core import AcousticDynamics
+from .neg_adj3 import AdjustNegativeTracerMixingRatio
 from .remapping import LagrangianToEulerian
 from .tracer_2d_1l import TracerAdvection
 
@@ -66,6 +67,9 @@ class DynamicalCore:
         self._hyperdiffusion = acoustic_misc.HyperdiffusionDamping(stencil_factory, qf, damping_coefficients,
                                                                    grid_data.rarea, config.nf_omega)
         self._cappa = self.acoustic_dynamics.cappa
+        self._adjust_tracer_mixing_ratio = AdjustNegativeTracerMixingRatio(
+            stencil_factory, quantity_factory=qf, check_negative=getattr(config, "check_negative", False),
+            hydrostatic=config.hydrostatic)
         self._lagrangian_to_eulerian_obj = LagrangianToEulerian(
             stencil_factory, qf, config.remapping, grid_data.area_64, NQ, None, self.tracers, checkpointer)
         self._omega_halo_updater = comm.get_scalar_halo_updater([qf.get_quantity_halo_spec(_C3)])
@@ -144,6 +148,7 @@ class DynamicalCore:
                     if self.config.nf_omega > 0:
                         self._omega_halo_updater.update([state.omga])
                         self._hyperdiffusion(state.omga, 0.18 * self._da_min)
-        # AdjustNegativeTracerMixingRatio (neg_adj3.py) — SURVEY.md §8f row 2, not implemented yet.
+        self._adjust_tracer_mixing_ratio(state.qvapor, state.qliquid, state.qrain, state.qsnow, state.qice, state.qgraupel,
+                                         state.qcld, state.pt, state.delp)
         self._c2l_updater.update([state.u], [state.v])
         rt.call("fv3_c2l_ord4", state.u.ptr, state.v.ptr, state.ua.ptr, state.va.ptr)
