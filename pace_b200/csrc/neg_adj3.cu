@@ -152,6 +152,9 @@ int fv3_neg_adj3(fv3_ctx *ctx, double *qvapor, double *qliquid, double *qrain, d
     for (int k = 0; k < km; ++k) {
       const int64_t o = c0 + k * sk;
       Water w{qvapor[o], qice[o], qsnow[o], qgraupel[o], qrain[o], qliquid[o], pt[o]};
+      cneg = cneg || qcld[o] < 0.0;
+      // a level whose six species are all non-negative comes out of fix_negative_ice / _liq unchanged
+      if (w.qvapor >= 0.0 && w.qice >= 0.0 && w.qsnow >= 0.0 && w.qgraupel >= 0.0 && w.qrain >= 0.0 && w.qliquid >= 0.0) continue;
       const double q_liq = 0.0 > w.qliquid + w.qrain ? 0.0 : w.qliquid + w.qrain;
       const double q_sol = 0.0 > w.qice + w.qsnow ? 0.0 : w.qice + w.qsnow;
       const double cpm = (1.0 - (w.qvapor + q_liq + q_sol)) * CV_AIR + w.qvapor * CV_VAP + q_liq * C_LIQ + q_sol * C_ICE;
@@ -167,7 +170,6 @@ int fv3_neg_adj3(fv3_ctx *ctx, double *qvapor, double *qliquid, double *qrain, d
       qliquid[o] = w.qliquid;
       pt[o] = w.pt;
       vneg = vneg || w.qvapor < 0.0;
-      cneg = cneg || qcld[o] < 0.0;
     }
     const double *dp = delp + c0;
     fillq_column(qgraupel + c0, dp, sk, km);
