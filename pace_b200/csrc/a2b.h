@@ -1,9 +1,8 @@
-// A-grid -> B-grid (cell corner) 4th-order interpolation, evaluated point by point.
-//   a2b_point <- AGrid2BGridFourthOrder.__call__ (fv3core/pace/fv3core/stencils/a2b_ord4.py:673-761):
+// A-grid -> B-grid (cell corner) 4th-order interpolation.
+//   a2b_plane <- AGrid2BGridFourthOrder.__call__ (fv3core/pace/fv3core/stencils/a2b_ord4.py:673-761):
 //                corner extrapolation (:37-273; great-circle weights precomputed on the host, fv3_grid.a2b_w),
 //                tile-edge formulas qout_x_edge / qout_y_edge (:286-311), ppm_volume_mean_x/y (:416-450) and
-//                a2b_interpolation (:453-481).  The reference's three temporaries (qx, qy, qout_edges) are
-//                recomputed from qin inside the thread.
+//                a2b_interpolation (:453-481).
 #pragma once
 #include "common.h"
 
@@ -111,35 +110,6 @@ FV_HD double a2b_edge_value(const fv3_geom &g, const fv3_grid &m, int s, Q q, in
   };
   const double es = (js ? m.edge_s : m.edge_n)[O2(s, i, 0)];
   return es * q1(i - 1) + (1.0 - es) * q1(i);
-}
-
-template <class Q>
-FV_HD double a2b_point(const fv3_geom &g, const fv3_grid &m, int s, Q q, int i, int j) {
-  const int isc = g.halo, iec = g.halo + g.nx - 1, jsc = g.halo, jec = g.halo + g.ny - 1;
-  const bool W = on_west(g, s), E = on_east(g, s), S = on_south(g, s), N = on_north(g, s);
-  if ((W && i == isc) || (E && i == iec + 1) || (S && j == jsc) || (N && j == jec + 1)) return a2b_edge_value(g, m, s, q, i, j);
-  auto qx = [&](int jj) { return a2b_qx(g, m, s, q, i, jj); };
-  auto qy = [&](int ii) { return a2b_qy(g, m, s, q, ii, j); };
-  double qxx, qyy;
-  if (S && j == jsc + 1) {
-    const double upper = A2B::a2 * (qx(j - 1) + qx(j + 2)) + A2B::a1 * (qx(j) + qx(j + 1));
-    qxx = A2B::c1 * (qx(j - 1) + qx(j)) + A2B::c2 * (a2b_edge_value(g, m, s, q, i, j - 1) + upper);
-  } else if (N && j == jec) {
-    const double lower = A2B::a2 * (qx(j - 3) + qx(j)) + A2B::a1 * (qx(j - 2) + qx(j - 1));
-    qxx = A2B::c1 * (qx(j - 1) + qx(j)) + A2B::c2 * (a2b_edge_value(g, m, s, q, i, j + 1) + lower);
-  } else {
-    qxx = A2B::a2 * (qx(j - 2) + qx(j + 1)) + A2B::a1 * (qx(j - 1) + qx(j));
-  }
-  if (W && i == isc + 1) {
-    const double right = A2B::a2 * (qy(i - 1) + qy(i + 2)) + A2B::a1 * (qy(i) + qy(i + 1));
-    qyy = A2B::c1 * (qy(i - 1) + qy(i)) + A2B::c2 * (a2b_edge_value(g, m, s, q, i - 1, j) + right);
-  } else if (E && i == iec) {
-    const double left = A2B::a2 * (qy(i - 3) + qy(i)) + A2B::a1 * (qy(i - 2) + qy(i - 1));
-    qyy = A2B::c1 * (qy(i - 1) + qy(i)) + A2B::c2 * (a2b_edge_value(g, m, s, q, i + 1, j) + left);
-  } else {
-    qyy = A2B::a2 * (qy(i - 2) + qy(i + 1)) + A2B::a1 * (qy(i - 1) + qy(i));
-  }
-  return 0.5 * (qxx + qyy);
 }
 
 // ---- plane-resident form (plane.h): the reference's three temporaries qx, qy, qout_edges are built ONCE per strip

@@ -70,7 +70,6 @@ FV_HD bool on_north(const fv3_geom &g, int s) { return g.edge[s] & FV3_EDGE_NORT
 
 FV_HD double dmin(double a, double b) { return a < b ? a : b; }
 FV_HD double dmax(double a, double b) { return a > b ? a : b; }
-FV_HD double dsign(double a, double b) { return b >= 0.0 ? fabs(a) : -fabs(a); }
 
 #ifndef FV3_HOSTSIM
 template <class F>

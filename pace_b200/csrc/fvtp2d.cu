@@ -14,20 +14,6 @@ namespace {
 
 constexpr int S_FYIN = 8, S_FXIN = 9, S_QI = 10, S_QJ = 11, S_DA = 12;  // scratch slots (12..15 = delnflux ping-pong)
 
-struct Idx {
-  int isc, iec, jsc, jec, ied, jed;
-};
-Idx make_idx(const fv3_geom &g) {
-  Idx x;
-  x.isc = g.halo;
-  x.iec = g.halo + g.nx - 1;
-  x.jsc = g.halo;
-  x.jec = g.halo + g.ny - 1;
-  x.ied = x.iec + g.halo;
-  x.jed = x.jec + g.halo;
-  return x;
-}
-
 // ---- plane-resident transport (see plane.h) ------------------------------------------------------------------
 // Shared-memory planes (each PL = nj * sj doubles, same (i, j) offsets as a global plane):
 //   Q : q, cube corners filled for the y sweep, then for the x sweep; later q advected along y (q_i)

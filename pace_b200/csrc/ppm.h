@@ -1,5 +1,6 @@
 // 1-D piecewise-parabolic "value advected through an interface" and cube-corner index remapping.
-//   ppm_flux  <- compute_x_flux / compute_y_flux (fv3core/pace/fv3core/stencils/xppm.py:249-266, yppm.py mirror):
+//   ppm_al_lt8 / ppm_blbr8 / ppm_flux_staged
+//             <- compute_x_flux / compute_y_flux (fv3core/pace/fv3core/stencils/xppm.py:249-266, yppm.py mirror):
 //                ord < 8: compute_al (:148-181) + get_flux (:64-71) with the monotonicity mask (:47-61);
 //                ord == 8: compute_blbr_ord8plus (:249-262) = dm/al/blbr (:82-102) + bl_br_edges (:185-246)
 //                          + pert_ppm_standard_constraint_fcn (ppm.py:22-36) + get_flux_ord8plus (:74-79)
@@ -35,25 +36,6 @@ FV_HD double ppm_al_lt8(Q q, DX dx, int i, const Edge1D &e) {
 
 FV_HD double ppm_fx1(double c, double br_l, double b0_l, double bl_r, double b0_r) {
   return c > 0.0 ? (1.0 - c) * (br_l - c * b0_l) : (1.0 + c) * (bl_r + c * b0_r);
-}
-
-template <class Q, class DX>
-FV_HD double ppm_flux_lt8(int mord, Q q, DX dx, double c, int i, const Edge1D &e) {
-  const double al0 = ppm_al_lt8(q, dx, i - 1, e), al1 = ppm_al_lt8(q, dx, i, e), al2 = ppm_al_lt8(q, dx, i + 1, e);
-  const double ql = q(i - 1), qr = q(i);
-  const double bl_l = al0 - ql, br_l = al1 - ql, b0_l = bl_l + br_l;
-  const double bl_r = al1 - qr, br_r = al2 - qr, b0_r = bl_r + br_r;
-  bool s_l, s_r;
-  if (mord == 5) {
-    s_l = bl_l * br_l < 0;
-    s_r = bl_r * br_r < 0;
-  } else {
-    s_l = (3.0 * fabs(b0_l)) < fabs(bl_l - br_l);
-    s_r = (3.0 * fabs(b0_r)) < fabs(bl_r - br_r);
-  }
-  const double mask = (s_l || s_r) ? 1.0 : 0.0;
-  const double fx1 = ppm_fx1(c, br_l, b0_l, bl_r, b0_r);
-  return c > 0.0 ? ql + fx1 * mask : qr + fx1 * mask;
 }
 
 template <class Q>
@@ -144,45 +126,8 @@ FV_HD void ppm_blbr8(Q q, DX dx, int i, const Edge1D &e, bool minmax, double &bl
   br = ar;
 }
 
-template <class Q, class DX>
-FV_HD double ppm_flux8(Q q, DX dx, double c, int i, const Edge1D &e, bool minmax) {
-  double bl, br;
-  if (c > 0.0) {
-    ppm_blbr8(q, dx, i - 1, e, minmax, bl, br);
-    const double b0 = bl + br;
-    return q(i - 1) + (1.0 - c) * (br - c * b0);
-  }
-  ppm_blbr8(q, dx, i, e, minmax, bl, br);
-  const double b0 = bl + br;
-  return q(i) + (1.0 + c) * (bl + c * b0);
-}
-
-// Same value as ppm_flux8, with the upwind cell selected first so that the (large) bl/br code exists once.
-template <class Q, class DX>
-FV_HD double ppm_flux8_upwind(Q q, DX dx, double c, int i, const Edge1D &e, bool minmax) {
-  const bool pos = c > 0.0;
-  const int cc = pos ? i - 1 : i;
-  double bl, br;
-  ppm_blbr8(q, dx, cc, e, minmax, bl, br);
-  const double b0 = bl + br;
-  return pos ? q(cc) + (1.0 - c) * (br - c * b0) : q(cc) + (1.0 + c) * (bl + c * b0);
-}
-
-// compile-time order: MORD = |hord| in {5, 6, 8}
-template <int MORD, class Q, class DX>
-FV_HD double ppm_flux_t(Q q, DX dx, double c, int i, const Edge1D &e) {
-  if (MORD < 8) return ppm_flux_lt8(MORD, q, dx, c, i, e);
-  return ppm_flux8_upwind(q, dx, c, i, e, true);
-}
-
-// ---- two-pass form used by the plane-resident kernels: pass 1 stores, per line, the edge values al (MORD < 8) or
-// the limited slopes dm (MORD == 8) ONCE per face / cell; pass 2 builds the interface value from them.  Same
-// expressions as ppm_flux_lt8 / ppm_blbr8, so the result is bit-identical to the one-pass form.
-template <int MORD, class Q, class DX>
-FV_HD double ppm_stage(Q q, DX dx, int i, const Edge1D &e) {
-  if (MORD < 8) return ppm_al_lt8(q, dx, i, e);
-  return ppm_dm8(q, i);
-}
+// ---- two-pass form used by the plane-resident kernels (sweep.h): pass 1 stores, per line, the edge values al
+// (MORD < 8) or the limited slopes dm (MORD == 8) ONCE per face / cell; pass 2 builds the interface value from them.
 // T: accessor of the staged values (al at face i / dm of cell i)
 template <int MORD, class Q, class T, class DX>
 FV_HD double ppm_flux_staged(Q q, T t, DX dx, double c, int i, const Edge1D &e) {
@@ -218,13 +163,6 @@ FV_HD double ppm_flux_staged(Q q, T t, DX dx, double c, int i, const Edge1D &e) 
   }
   const double b0 = bl + br;
   return pos ? qc + (1.0 - c) * (br - c * b0) : qc + (1.0 + c) * (bl + c * b0);
-}
-
-template <class Q, class DX>
-FV_HD double ppm_flux(int ord, Q q, DX dx, double c, int i, const Edge1D &e, bool minmax) {
-  const int mord = ord < 0 ? -ord : ord;
-  if (mord < 8) return ppm_flux_lt8(mord, q, dx, c, i, e);
-  return ppm_flux8(q, dx, c, i, e, minmax);
 }
 
 // copy_corners_x: a cell in a cube-corner halo block at outward distances (a, b) reads the cell at
