@@ -33,3 +33,39 @@ def test_forced_strips_hostsim(device, n_strips):
 @pytest.mark.gpu
 def test_forced_strips_gpu():
     _run(2, "gpu")
+
+
+_C48_SCRIPT = r"""
+import hashlib, sys
+import numpy as np
+sys.path.insert(0, %r)
+from oracle import hostsim
+hostsim.install(openmp=True)
+from tests.test_c48_step import _build
+dycore, state = _build("cpu")
+dycore.step_dynamics(state)
+out = state.as_numpy()
+h = hashlib.sha1()
+for n in ("u", "v", "w", "delp", "pt", "delz", "qvapor"):
+    h.update(np.ascontiguousarray(out[n]).tobytes())
+print("DIGEST", h.hexdigest())
+"""
+
+
+def _c48_digest(n_strips):
+    env = dict(os.environ)
+    env.pop("FV3_FORCE_STRIPS", None)
+    if n_strips:
+        env["FV3_FORCE_STRIPS"] = str(n_strips)
+    r = subprocess.run([sys.executable, "-c", _C48_SCRIPT % ROOT], cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return [l for l in r.stdout.splitlines() if l.startswith("DIGEST")][0]
+
+
+def test_c48_strip_count_does_not_change_a_bit(device):
+    """48 x 48 subdomains: the launcher's own choice (2 strips of 24 rows for the 5-plane kernels), one strip and 5
+    strips of 10 rows give the same timestep bit for bit (host simulation of the kernel sources)."""
+    if device != "cpu":
+        pytest.skip("host simulation is exercised on CPU-only boxes")
+    auto, one, five = _c48_digest(0), _c48_digest(1), _c48_digest(5)
+    assert auto == one == five
