@@ -44,3 +44,41 @@ def compute_geopotential(ix: Idx, zh, gz):
     """dyn_core.py:115-117 on compute + 2 halo, nz+1 levels."""
     si, sj = sl(ix.isc - 2, ix.iec + 2), sl(ix.jsc - 2, ix.jec + 2)
     gz[si, sj, : ix.nz + 1] = zh[si, sj, : ix.nz + 1] * GRAV
+
+
+def edge_pe(ix: Idx, pe, delp, ptop):
+    """edge_pe (pe_halo.py:6-34): interface pressure in the 1-cell ring around the compute domain."""
+    for i in range(ix.isc - 1, ix.iec + 2):
+        for j in range(ix.jsc - 1, ix.jec + 2):
+            if ix.isc <= i <= ix.iec and ix.jsc <= j <= ix.jec:
+                continue
+            pe[i, j, 0] = ptop
+            for k in range(1, ix.nz + 1):
+                pe[i, j, k] = pe[i, j, k - 1] + delp[i, j, k - 1]
+
+
+def pk3_halo(ix: Idx, pk3, delp, ptop, akap):
+    """PK3Halo.__call__ (pk3_halo.py:11-69): pk3 = pe ** akap in the 2-cell ring around the compute domain."""
+    for i in range(ix.isc - 2, ix.iec + 3):
+        for j in range(ix.jsc - 2, ix.jec + 3):
+            if ix.isc <= i <= ix.iec and ix.jsc <= j <= ix.jec:
+                continue
+            p = ptop
+            for k in range(1, ix.nz + 1):
+                p = p + delp[i, j, k - 1]
+                pk3[i, j, k] = p ** akap
+
+
+def apply_diffusive_heating(ix: Idx, delp, delz, cappa, heat_source, pt, delt_time_factor):
+    """apply_diffusive_heating (temperature_adjust.py:8-43), compute domain, pt in place."""
+    from .constants import CV_AIR, RDG
+
+    si, sj, K = sl(ix.isc, ix.iec), sl(ix.jsc, ix.jec), slice(0, ix.nz)
+    pkz = (RDG * delp[si, sj, K] / delz[si, sj, K] * pt[si, sj, K]) ** (cappa[si, sj, K] / (1.0 - cappa[si, sj, K]))
+    dtmp = heat_source[si, sj, K] / (CV_AIR * delp[si, sj, K])
+    lim = np.full(ix.nz, delt_time_factor)
+    lim[0] = delt_time_factor * 0.1
+    lim[1] = delt_time_factor * 0.5
+    mag = np.minimum(lim[None, None, :], np.abs(dtmp))
+    deltmin = np.where(dtmp > 0, np.abs(mag), -np.abs(mag))
+    pt[si, sj, K] = pt[si, sj, K] + deltmin / pkz

@@ -90,3 +90,46 @@ def riem_solver_c(dt2, cappa, ptop, hs, ws, ptc, q_con, delpc, gz, pef, w3, p_fa
     gz[si, sj, nz] = hs[si, sj]
     for k in range(nz - 1, -1, -1):
         gz[si, sj, k] = gz[si, sj, k + 1] - dz[:, :, k] * GRAV
+
+
+def riem_solver3(last_call, dt, cappa, ptop, zs, ws, delz, q_con, delp, pt, zh, pe, ppe, pk3, pk, peln, w, p_fac, nx, ny, nz,
+                 halo=3):
+    """NonhydrostaticVerticalSolver.__call__ (riem_solver3.py:207-321): precompute (:26-90), Sim1Solver, finalize
+    (:93-145); compute domain; delz, zh, w, ppe, pk3 (and pe, pk, peln on the last call) updated in place."""
+    from .constants import KAPPA
+
+    si = slice(halo, halo + nx)
+    sj = slice(halo, halo + ny)
+    dm = delp[si, sj, :nz].copy()
+    sh = dm.shape[:2]
+    pem = np.zeros(sh + (nz + 1,))
+    peg = np.zeros_like(pem)
+    pem[:, :, 0] = ptop
+    peg[:, :, 0] = ptop
+    for k in range(1, nz + 1):
+        pem[:, :, k] = pem[:, :, k - 1] + dm[:, :, k - 1]
+        peg[:, :, k] = peg[:, :, k - 1] + dm[:, :, k - 1] * (1.0 - q_con[si, sj, k - 1])
+    peln1 = np.log(ptop)
+    pelng = np.log(peg)
+    pelng[:, :, 0] = peln1
+    lp = np.log(pem)
+    lp[:, :, 0] = peln1
+    pk3v = np.exp(KAPPA * lp)
+    pk3v[:, :, 0] = np.exp(KAPPA * peln1)
+    pk3[si, sj, : nz + 1] = pk3v
+    if last_call:
+        peln[si, sj, : nz + 1] = lp
+        pk[si, sj, : nz + 1] = pk3v
+        pe[si, sj, : nz + 1] = pem
+    pm = (peg[:, :, 1:] - peg[:, :, :nz]) / (pelng[:, :, 1:] - pelng[:, :, :nz])
+    dz = zh[si, sj, 1 : nz + 1] - zh[si, sj, :nz]
+    gm = 1.0 / (1.0 - cappa[si, sj, :nz])
+    dm = dm * (1.0 / GRAV)
+    wv = w[si, sj, :nz].copy()
+    pp = sim1_solver(wv, dm, gm, dz, pt[si, sj, :nz], pm, pem, ws[si, sj], cappa[si, sj, :nz], dt, p_fac)
+    w[si, sj, :nz] = wv
+    delz[si, sj, :nz] = dz
+    ppe[si, sj, : nz + 1] = pp
+    zh[si, sj, nz] = zs[si, sj]
+    for k in range(nz - 1, -1, -1):
+        zh[si, sj, k] = zh[si, sj, k + 1] - dz[:, :, k]

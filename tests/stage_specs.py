@@ -319,15 +319,41 @@ def _n_riem3(sf, qf, rt, q, d):
            q["pt"], q["zh"], q["p"], q["ppe"], q["pk3"], q["pk"], q["log_p_interface"], q["w"])
 
 
-register(StageSpec("riem_solver3", "Riem_Solver3#0", ("delz", "zh", "w", "p", "ppe", "pk3", "pk", "log_p_interface"), _o_todo,
+def _o_riem3(ix, g, a):
+    from oracle import riem_solver as O
+
+    O.riem_solver3(bool(a["last_call"]), float(a["dt"]), a["cappa"], float(a["ptop"]), a["zs"], a["ws"], a["delz"], a["q_con"],
+                   a["delp"], a["pt"], a["zh"], a["p"], a["ppe"], a["pk3"], a["pk"], a["log_p_interface"], a["w"], 0.05,
+                   ix.nx, ix.ny, ix.nz)
+
+
+register(StageSpec("riem_solver3", "Riem_Solver3#0", ("delz", "zh", "w", "p", "ppe", "pk3", "pk", "log_p_interface"), _o_riem3,
                    _n_riem3, tol=1e-11, near_zero=1e-12, check_untouched=False, case=S2,
                    # w is a small difference of large terms: the reference itself allows 5e-6 for this routine on every
                    # backend (fv3core/tests/savepoint/translate/overrides/standard.yaml, Riem_Solver3)
                    tols={"w": 5e-6},
                    regions={n: COMPUTE for n in ("delz", "zh", "w", "p", "ppe", "pk3", "pk", "log_p_interface")}))
-register(StageSpec("edge_pe", "PE_Halo#0", ("pe",), _o_todo,
+def _o_edge_pe(ix, g, a):
+    from oracle import dyn_core as O
+
+    O.edge_pe(ix, a["pe"], a["delp"], float(a["ptop"]))
+
+
+def _o_pk3_halo(ix, g, a):
+    from oracle import dyn_core as O
+
+    O.pk3_halo(ix, a["pk3"], a["delp"], float(a["ptop"]), float(a["akap"]))
+
+
+def _o_diffusive_heating(ix, g, a):
+    from oracle import dyn_core as O
+
+    O.apply_diffusive_heating(ix, a["delp"], a["delz"], a["cappa"], a["heat_source"], a["pt"], float(a["delt_time_factor"]))
+
+
+register(StageSpec("edge_pe", "PE_Halo#0", ("pe",), _o_edge_pe,
                    lambda sf, qf, rt, q, d: rt.call("fv3_edge_pe", q["pe"].ptr, q["delp"].ptr, f(d, "ptop")), case=S2))
-register(StageSpec("pk3_halo", "PK3_Halo#0", ("pk3",), _o_todo,
+register(StageSpec("pk3_halo", "PK3_Halo#0", ("pk3",), _o_pk3_halo,
                    lambda sf, qf, rt, q, d: rt.call("fv3_pk3_halo", q["pk3"].ptr, q["delp"].ptr, f(d, "ptop"), f(d, "akap")),
                    tol=1e-13, case=S2))
 register(StageSpec("nh_p_grad", "NH_P_Grad#0", ("u", "v", "pp", "gz", "pk3"), _o_todo,
@@ -358,7 +384,7 @@ register(StageSpec("del2cubed_heat", "Del2Cubed#0", ("qdel",), _o_todo, _n_del2(
                    regions={"qdel": COMPUTE}))
 register(StageSpec("del2cubed_omga", "Del2Cubed#1", ("qdel",), _o_todo, _n_del2(1), tol=1e-13, case=S2,
                    regions={"qdel": COMPUTE}))
-register(StageSpec("diffusive_heating", "DiffusiveHeating#0", ("pt",), _o_todo,
+register(StageSpec("diffusive_heating", "DiffusiveHeating#0", ("pt",), _o_diffusive_heating,
                    lambda sf, qf, rt, q, d: rt.call("fv3_apply_diffusive_heating", q["delp"].ptr, q["delz"].ptr, q["cappa"].ptr,
                                                     q["heat_source"].ptr, q["pt"].ptr, f(d, "delt_time_factor"), NZ),
                    tol=1e-13, case=S2, regions={"pt": COMPUTE}))
@@ -398,8 +424,14 @@ def _make_map_single(n, iv, i_extra=0, j_extra=0):
         rt.call("fv3_map_single", q["q1"].ptr, q["pe1"].ptr, q["pe2"].ptr, qs.ptr if (qs is not None and iv == -2) else None,
                 1, float(d.get("in.qmin", 0.0)), 9, iv, i_extra, j_extra)
 
+    def oracle(ix, g, a):
+        from oracle import remap as O
+
+        O.map_single(a["q1"], a["pe1"], a["pe2"], a.get("qs") if iv == -2 else None, float(a.get("qmin", 0.0)), iv,
+                     ix.nx, ix.ny, ix.nz, i_extra, j_extra)
+
     reg = (slice(3, 3 + NX + i_extra), slice(3, 3 + NX + j_extra))
-    SPECS[f"map_single_{n}"] = StageSpec(f"map_single_{n}", f"MapSingle#{n}", ("q1",), _o_todo, native, tol=1e-12, near_zero=1e-13,
+    SPECS[f"map_single_{n}"] = StageSpec(f"map_single_{n}", f"MapSingle#{n}", ("q1",), oracle, native, tol=1e-12, near_zero=1e-13,
                                          case=S2, regions={"q1": reg}, check_untouched=False)
 
 
@@ -417,7 +449,14 @@ def _n_fillz(sf, qf, rt, q, d):
     rt.call("fv3_fillz", arr.data_ptr(), 8, q["dp2"].ptr)
 
 
-SPECS["fillz"] = StageSpec("fillz", "Fillz#0", tuple("tracers." + n for n in ("qvapor", "qliquid", "qrain", "qice")), _o_todo,
+def _o_fillz(ix, g, a):
+    from oracle import remap as O
+
+    for n in ["qvapor", "qliquid", "qrain", "qice", "qsnow", "qgraupel", "qo3mr", "qsgs_tke"]:
+        O.fillz(a["tracers." + n], a["dp2"], ix.nx, ix.ny, ix.nz)
+
+
+SPECS["fillz"] = StageSpec("fillz", "Fillz#0", tuple("tracers." + n for n in ("qvapor", "qliquid", "qrain", "qice")), _o_fillz,
                            _n_fillz, tol=5e-6, case=S2, regions={"tracers." + n: COMPUTE for n in ("qvapor", "qliquid", "qrain", "qice")},
                            check_untouched=False)
 

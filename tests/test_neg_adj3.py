@@ -47,6 +47,17 @@ def _check(dev):
         np.testing.assert_array_equal(out[n], pos[n], err_msg=n)
 
 
+def test_oracle_neg_adj3_matches_reference():
+    """The Python restatement (oracle/neg_adj3.py) against the reference's own output."""
+    from oracle import neg_adj3 as O
+
+    z = np.load(os.path.join(H.GOLDEN, "neg_adj3", "case0.npz"))
+    a = {n: z["in." + n].copy() for n in NAMES}
+    O.neg_adj3(*[a[n] for n in NAMES])
+    for n in NAMES:
+        H.assert_close(a[n], z["out." + n], max_error=1e-13, near_zero=1e-25, name=n)
+
+
 def test_neg_adj3_hostsim(device):
     if device != "cpu":
         pytest.skip("host simulation is exercised on CPU-only boxes")
