@@ -48,8 +48,8 @@ def _check(dev):
 
 
 def test_oracle_neg_adj3_matches_reference():
-    """The Python restatement (oracle/neg_adj3.py) against the reference's own output."""
-    from oracle import neg_adj3 as O
+    """The Python restatement (oracle/negative_water.py) against the reference's own output."""
+    from oracle import negative_water as O
 
     z = np.load(os.path.join(H.GOLDEN, "neg_adj3", "case0.npz"))
     a = {n: z["in." + n].copy() for n in NAMES}
