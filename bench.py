@@ -27,6 +27,7 @@ if ROOT not in sys.path:
 STAGE_PASSES = {
     "fv3_c_sw": 15, "fv3_update_dz_c": 4, "fv3_riem_solver_c": 8, "fv3_p_grad_c": 7, "fv3_d_sw": 34,
     "fv3_update_dz_d": 6, "fv3_riem_solver3": 13, "fv3_nh_p_grad": 8, "fv3_ray_fast": 6,
+    "fv3_tracer_subcycle": 25,   # one sub-cycle: 8 shared reads + dp2 write + 8 x (tracer read + write)
 }
 SUBSTEP_PASSES, TRACER_PASSES, REMAP_PASSES, EXTRA_BYTES_PER_CELL = 101, 85, 36, 100
 
