@@ -3,8 +3,9 @@
 //                        XPiecewiseParabolic / YPiecewiseParabolic (xppm.py:269-353, yppm.py) and, when a damping
 //                        column is given, DelnFlux.__call__ (delnflux.py:1164-1207)
 //   fv3_delnflux_nosg <- DelnFluxNoSG.__call__ (delnflux.py:1209-1261)
-// 10 + (7 + 6*nmax) reference launches become 3 + (2 + nmax): the corner copies are index remaps at read time
-// (ppm.h), the Laplacian d2 of each del-n iteration is recomputed from the previous fluxes instead of stored.
+//   fv3_tracer_subcycle <- one sub-cycle of TracerAdvection.__call__ for all tracers (tracer_2d_1l.py:341-392)
+// The 10 + (7 + 6*nmax) reference launches of a transport with damping are ONE strip-resident kernel (plane.h): the
+// corner copies are index remaps at read time (ppm.h), every intermediate lives in shared memory.
 #include "common.h"
 #include "plane.h"
 #include "ppm.h"
@@ -12,10 +13,8 @@
 
 namespace {
 
-constexpr int S_FYIN = 8, S_FXIN = 9, S_QI = 10, S_QJ = 11, S_DA = 12;  // scratch slots (12..15 = delnflux ping-pong)
-
 // ---- plane-resident transport (see plane.h) ------------------------------------------------------------------
-// Shared-memory planes (each PL = nj * sj doubles, same (i, j) offsets as a global plane):
+// Shared-memory planes of the strip (Block::plane(n): resident rows x sj doubles, same (i, j) offsets as a global plane):
 //   Q : q, cube corners filled for the y sweep, then for the x sweep; later q advected along y (q_i)
 //   A : inner y-sweep interface values (fy_in); finally the y flux
 //   B : inner x-sweep interface values (fx_in); finally the x flux
