@@ -1,0 +1,144 @@
+"""Layout (2,2) — the decomposition of the C128 benchmark — end to end against the reference: c24 L79, 24 subdomains of
+12 x 12 cells in one process, ONE step_dynamics (k_split = n_split = 1, the c12 dycore_config).  Several subdomains per
+tile exercise what layout (1,1) cannot: subdomains without tile edges, halo exchange between subdomains of one tile
+and across rotated tile edges from interior positions, corner neighbours.
+
+As in tests/test_c48_step.py nothing of the reference is fed in (own grid generator, own analytic initial state); the
+committed reference data (tests/golden/c24L2_step, from the unmodified reference's numpy backend run on 24 thread-ranks
+by oracle/refshim/gen_golden.py, reduced by tests/golden/make_layout2_step.py) hold four ranks on four tiles before
+and after the step on a subsample of levels.  Tolerances and the bounded wind-outlier allowance are those of
+tests/test_c48_step.py (same reason: the initial winds agree to 1e-12 m/s, not bit for bit); the cell-centred winds ua,
+va are 4-point interpolations of u, v, so one flipped column touches more of a 12 x 12 subdomain: 8 % of the points,
+each still within 1e-2 m/s.  The strict form — reference grid and initial state in, every field of all 24 ranks at
+the c12 tolerances — runs whenever the full dump is present ($PACE_B200_GOLDEN_CACHE/c24L2; build container) and passes.
+"""
+import json
+import os
+from datetime import timedelta
+
+import numpy as np
+import pytest
+
+from tests import helpers as H
+from tests.test_c48_step import WIND_OUTLIERS
+from tests.test_dycore_step import TOL
+
+BASE = os.path.join(H.GOLDEN, "c24L2_step")
+NX = 12  # cells per subdomain edge
+OUTLIERS = dict(WIND_OUTLIERS, ua=(0.08, 1e-2), va=(0.08, 1e-2))
+
+
+def _build(dev):
+    from pace_b200.fv3core._config import baroclinic_config
+    from pace_b200.fv3core.initialization import baroclinic
+    from pace_b200.fv3core.runtime import Runtime
+    from pace_b200.fv3core.stencil_factory import GridIndexing, StencilFactory
+    from pace_b200.fv3core.stencils.fv_dynamics import DynamicalCore
+    from pace_b200.util.grid.helper import DampingCoefficients, GridData
+
+    comm, qf = H.make_comm(24, 2, 79, dev)
+    gd = GridData.new_from_generation(qf, comm)
+    damp = DampingCoefficients.new_from_generation(qf, gd)
+    cfg = baroclinic_config(24, (2, 2), n_split=1, k_split=1)
+    rt = Runtime(comm, qf, gd, damp, cfg)
+    sf = StencilFactory(None, GridIndexing.from_sizer_and_communicator(qf.sizer, comm), rt)
+    state = baroclinic.init_baroclinic_state(gd, qf, adiabatic=False, hydrostatic=False, moist_phys=True, comm=comm)
+    dycore = DynamicalCore(comm, gd, sf, qf, damp, cfg, state.phis, state, timedelta(seconds=cfg.dt_atmos))
+    return dycore, state
+
+
+def _compare(out, ref, levels, fields, tol, what, outliers=None):
+    failures = []
+    for name in fields:
+        rel, floor = tol(name)
+        for r, z in ref.items():
+            a, b = out[name][r], z[name]
+            if a.ndim == 3:
+                ii = slice(3, 3 + NX + (1 if name == "v" else 0))
+                jj = slice(3, 3 + NX + (1 if name == "u" else 0))
+                a, b = a[ii, jj][:, :, levels], b[ii, jj]
+            else:
+                a, b = a[3:3 + NX, 3:3 + NX], b[3:3 + NX, 3:3 + NX]
+            m = H.ref_metric(a, b)
+            bad = (m > rel) & (np.abs(a - b) > floor)
+            if outliers and name in outliers and bad.any():
+                frac, dmax = outliers[name]
+                if bad.mean() <= frac and np.abs(a - b).max() <= dmax:
+                    continue
+            if bad.any():
+                failures.append(f"{what} {name} rank {r}: {int(bad.sum())} pts, worst rel {m[bad].max():.2e}, "
+                                f"worst abs {np.abs(a - b)[bad].max():.2e}")
+    assert not failures, "\n".join(failures)
+
+
+def _run(dev):
+    if not os.path.exists(os.path.join(BASE, "meta.json")):
+        pytest.skip("c24 layout (2,2) reference data not available")
+    meta = json.load(open(os.path.join(BASE, "meta.json")))
+    levels, fields, ranks = meta["levels"], meta["fields"], meta["ranks"]
+    ref0 = {r: dict(np.load(os.path.join(BASE, f"state0_rank{r}.npz"))) for r in ranks}
+    ref1 = {r: dict(np.load(os.path.join(BASE, f"state1_rank{r}.npz"))) for r in ranks}
+    dycore, state = _build(dev)
+    init_fields = [n for n in fields if n not in ("ua", "va", "omga")]
+    _compare(state.as_numpy(), ref0, levels, init_fields, lambda n: (1e-12, 1e-11 if n in ("u", "v") else 1e-13), "initial")
+    dycore.step_dynamics(state)
+    H.sync()
+    _compare(state.as_numpy(), ref1, levels, fields, lambda n: TOL.get(n, TOL["default"]), "after one step", OUTLIERS)
+
+
+def test_layout2_strict_with_reference_inputs_hostsim(device):
+    """All 24 ranks, every field, c12 tolerances, from the reference's own grid and initial state (needs the full dump)."""
+    if device != "cpu":
+        pytest.skip("host simulation is exercised on CPU-only boxes")
+    base = os.path.join(H.CACHE, "c24L2")
+    if not os.path.exists(os.path.join(base, "state1_rank23.npz")):
+        pytest.skip("full c24 layout (2,2) reference dump not present (oracle/refshim/gen_golden.py --nx 24 --layout 2 --capture-ranks)")
+    from pace_b200.fv3core._config import baroclinic_config
+    from pace_b200.fv3core.dycore_state import DycoreState
+    from pace_b200.fv3core.runtime import Runtime
+    from pace_b200.fv3core.stencil_factory import GridIndexing, StencilFactory
+    from pace_b200.fv3core.stencils.fv_dynamics import DynamicalCore
+    from pace_b200.util.grid.helper import DampingCoefficients, GridData
+    from tests.test_dycore_step import FIELDS
+
+    grids = [dict(np.load(os.path.join(base, f"grid_rank{r}.npz"))) for r in range(24)]
+    s0 = [dict(np.load(os.path.join(base, f"state0_rank{r}.npz"))) for r in range(24)]
+    comm, qf = H.make_comm(24, 2, 79, device)
+    gd = GridData.from_arrays(qf, grids)
+    damp = DampingCoefficients.from_arrays(qf, grids)
+    cfg = baroclinic_config(24, (2, 2), n_split=1, k_split=1)
+    rt = Runtime(comm, qf, gd, damp, cfg)
+    sf = StencilFactory(None, GridIndexing.from_sizer_and_communicator(qf.sizer, comm), rt)
+    state = DycoreState.init_from_numpy_arrays(s0, qf)
+    dycore = DynamicalCore(comm, gd, sf, qf, damp, cfg, state.phis, state, timedelta(seconds=cfg.dt_atmos))
+    dycore.step_dynamics(state)
+    H.sync()
+    out = state.as_numpy()
+    failures = []
+    for name in FIELDS:
+        rel, floor = TOL.get(name, TOL["default"])
+        for r in range(24):
+            a, b = out[name][r], np.load(os.path.join(base, f"state1_rank{r}.npz"))[name]
+            if a.ndim == 3:
+                nk = 80 if name in ("pe", "peln", "pk") else 79
+                ii = slice(3, 3 + NX + (1 if name == "v" else 0))
+                jj = slice(3, 3 + NX + (1 if name == "u" else 0))
+                a, b = a[ii, jj, :nk], b[ii, jj, :nk]
+            else:
+                a, b = a[3:3 + NX, 3:3 + NX], b[3:3 + NX, 3:3 + NX]
+            m = H.ref_metric(a, b)
+            bad = (m > rel) & (np.abs(a - b) > floor)
+            if bad.any():
+                failures.append(f"{name} rank {r}: {int(bad.sum())} pts, worst rel {m[bad].max():.2e}")
+    assert not failures, "\n".join(failures)
+
+
+def test_layout2_step_matches_reference_hostsim(device):
+    if device != "cpu":
+        pytest.skip("host simulation is exercised on CPU-only boxes")
+    _run(device)
+
+
+@pytest.mark.gpu
+def test_layout2_step_matches_reference_gpu(device):
+    _run(device)
