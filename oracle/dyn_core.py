@@ -82,3 +82,45 @@ def apply_diffusive_heating(ix: Idx, delp, delz, cappa, heat_source, pt, delt_ti
     mag = np.minimum(lim[None, None, :], np.abs(dtmp))
     deltmin = np.where(dtmp > 0, np.abs(mag), -np.abs(mag))
     pt[si, sj, K] = pt[si, sj, K] + deltmin / pkz
+
+
+def del2cubed(ix: Idx, g, qdel, cd, nmax):
+    """HyperdiffusionDamping.__call__ (del2cubed.py:165-194): corner_fill (:25-65), copy_corners_x / _y
+    (stencils/corners.py:307-425), compute_zonal / meridional_flux (:15-22), update_q (:72-76); qdel in place."""
+    from .fvtp2d import copy_corners_x, copy_corners_y
+
+    K = slice(0, ix.nz)
+    third = 1.0 / 3.0
+    ntimes = int(min(3, nmax))
+    isc, iec, jsc, jec = ix.isc, ix.iec, ix.jsc, ix.jec
+    for n in range(ntimes):
+        nt = ntimes - (n + 1)
+        q = qdel.copy()                                                     # corner_fill
+        qi = qdel
+        for (i, j, pts) in (
+                (isc, jsc, ((0, 0), (-1, 0), (0, -1))), (isc - 1, jsc, ((1, 0), (0, 0), (1, -1))),
+                (isc, jsc - 1, ((0, 1), (-1, 1), (0, 0))),
+                (iec, jsc, ((0, 0), (1, 0), (0, -1))), (iec + 1, jsc, ((-1, 0), (0, 0), (-1, -1))),
+                (iec, jsc - 1, ((0, 1), (1, 1), (0, 0))),
+                (iec, jec, ((0, 0), (1, 0), (0, 1))), (iec + 1, jec, ((-1, 0), (0, 0), (-1, 1))),
+                (iec, jec + 1, ((0, -1), (1, -1), (0, 0))),
+                (isc, jec, ((0, 0), (-1, 0), (0, 1))), (isc - 1, jec, ((1, 0), (0, 0), (1, 1))),
+                (isc, jec + 1, ((0, -1), (-1, -1), (0, 0)))):
+            (a, b, c_) = pts
+            if not ((ix.west if i <= isc else ix.east) and (ix.south if j <= jsc else ix.north)):
+                continue
+            q[i, j, K] = (qi[i + a[0], j + a[1], K] + qi[i + b[0], j + b[1], K] + qi[i + c_[0], j + c_[1], K]) * third
+        if nt > 0:
+            copy_corners_x(ix, q, K)
+        si, sj = sl(isc - nt, iec + nt + 1), sl(jsc - nt, jec + nt)
+        fx = np.zeros_like(q)
+        fx[si, sj, K] = g["damp_del6_v"][si, sj, None] * (_sh(q, -1, 0, si, sj)[:, :, K] - q[si, sj, K])
+        if nt > 0:
+            copy_corners_y(ix, q, K)
+        si, sj = sl(isc - nt, iec + nt), sl(jsc - nt, jec + nt + 1)
+        fy = np.zeros_like(q)
+        fy[si, sj, K] = g["damp_del6_u"][si, sj, None] * (_sh(q, 0, -1, si, sj)[:, :, K] - q[si, sj, K])
+        qdel[:, :, K] = q[:, :, K]
+        si, sj = sl(isc - nt, iec + nt), sl(jsc - nt, jec + nt)
+        qdel[si, sj, K] = qdel[si, sj, K] + cd * g["rarea"][si, sj, None] * (
+            fx[si, sj, K] - _sh(fx, 1, 0, si, sj)[:, :, K] + fy[si, sj, K] - _sh(fy, 0, 1, si, sj)[:, :, K])

@@ -380,9 +380,18 @@ def _n_del2(nmax):
     return native
 
 
-register(StageSpec("del2cubed_heat", "Del2Cubed#0", ("qdel",), _o_todo, _n_del2(3), tol=1e-13, case=S2,
+def _o_del2(nmax):
+    def oracle(ix, g, a):
+        from oracle import dyn_core as O
+
+        O.del2cubed(ix, g, a["qdel"], float(a["cd"]), nmax)
+
+    return oracle
+
+
+register(StageSpec("del2cubed_heat", "Del2Cubed#0", ("qdel",), _o_del2(3), _n_del2(3), tol=1e-13, case=S2,
                    regions={"qdel": COMPUTE}))
-register(StageSpec("del2cubed_omga", "Del2Cubed#1", ("qdel",), _o_todo, _n_del2(1), tol=1e-13, case=S2,
+register(StageSpec("del2cubed_omga", "Del2Cubed#1", ("qdel",), _o_del2(1), _n_del2(1), tol=1e-13, case=S2,
                    regions={"qdel": COMPUTE}))
 register(StageSpec("diffusive_heating", "DiffusiveHeating#0", ("pt",), _o_diffusive_heating,
                    lambda sf, qf, rt, q, d: rt.call("fv3_apply_diffusive_heating", q["delp"].ptr, q["delz"].ptr, q["cappa"].ptr,
