@@ -124,3 +124,38 @@ def del2cubed(ix: Idx, g, qdel, cd, nmax):
         si, sj = sl(isc - nt, iec + nt), sl(jsc - nt, jec + nt)
         qdel[si, sj, K] = qdel[si, sj, K] + cd * g["rarea"][si, sj, None] * (
             fx[si, sj, K] - _sh(fx, 1, 0, si, sj)[:, :, K] + fy[si, sj, K] - _sh(fy, 0, 1, si, sj)[:, :, K])
+
+
+def ray_fast(ix: Idx, u, v, w, dp, pfull, dt, ptop, rf_cutoff, tau, hydrostatic=False):
+    """RayleighDamping.__call__ (ray_fast.py:184-206) = ray_fast_wind_compute (:48-141): damping factors rf (:27-41),
+    reference pressure p_ref summed over the nudged levels, momentum lost by u / v redistributed over those levels;
+    u on (nx, ny+1), v on (nx+1, ny), w on (nx, ny); in place."""
+    import math
+
+    nz = ix.nz
+    nudge = rf_cutoff + min(100.0, 10.0 * ptop)
+    rf = np.ones(nz)
+    damped = pfull[:nz] < rf_cutoff
+    for k in range(nz):
+        if damped[k]:
+            val = dt / (tau * 86400.0) * math.sin(0.5 * math.pi * math.log(rf_cutoff / pfull[k]) / math.log(rf_cutoff / ptop)) ** 2
+            rf[k] = 1.0 / (1.0 + val)
+    p_ref = 0.0
+    for k in range(nz):
+        if pfull[k] < nudge:
+            p_ref = dp[k] if k == 0 else p_ref + dp[k]
+    for q, si, sj in ((u, sl(ix.isc, ix.iec), sl(ix.jsc, ix.jec + 1)), (v, sl(ix.isc, ix.iec + 1), sl(ix.jsc, ix.jec))):
+        dm = None
+        for k in range(nz):
+            if damped[k]:
+                d = (1.0 - rf[k]) * dp[k] * q[si, sj, k]
+                dm = d if dm is None else dm + d
+                q[si, sj, k] = q[si, sj, k] * rf[k]
+        for k in range(nz):
+            if pfull[k] < nudge and dm is not None:
+                q[si, sj, k] = q[si, sj, k] + dm / p_ref
+    if not hydrostatic:
+        si, sj = sl(ix.isc, ix.iec), sl(ix.jsc, ix.jec)
+        for k in range(nz):
+            if damped[k]:
+                w[si, sj, k] = w[si, sj, k] * rf[k]

@@ -369,7 +369,13 @@ def _n_ray(sf, qf, rt, q, d):
     RayleighDamping(sf, 3000.0, 10.0, False)(q["u"], q["v"], q["w"], None, None, f(d, "dt"), f(d, "ptop"))
 
 
-register(StageSpec("ray_fast", "Ray_Fast#0", ("u", "v", "w"), _o_todo, _n_ray, tol=1e-13, case=S2,
+def _o_ray(ix, g, a):
+    from oracle import dyn_core as O
+
+    O.ray_fast(ix, a["u"], a["v"], a["w"], a["dp"], a["pfull"], float(a["dt"]), float(a["ptop"]), 3000.0, 10.0)
+
+
+register(StageSpec("ray_fast", "Ray_Fast#0", ("u", "v", "w"), _o_ray, _n_ray, tol=1e-13, case=S2,
                    regions={"u": _YI, "v": _XI, "w": COMPUTE}, check_untouched=False))
 
 
