@@ -241,3 +241,21 @@ def fillz(q, dp, nx, ny, km, halo=3):
                 for k in range(1, km):
                     qc[k] = max(fac * dm[k] / d[k], 0.0)
             q[i, j, :km] = qc
+
+
+def fv_setup(qvapor, qliquid, qrain, qsnow, qice, qgraupel, q_con, cvm, pkz, pt, cappa, delp, delz, dp1, nx, ny, nz, halo=3):
+    """fv_setup (moist_cv.py:175-234, moist_phys) with moist_cv_nwat6_fn (:32-53); compute domain; outputs in place."""
+    from .constants import C_ICE, C_LIQ, CV_AIR, CV_VAP, RDG, RDGAS, ZVIR
+
+    s = (slice(halo, halo + nx), slice(halo, halo + ny), slice(0, nz))
+    ql = qliquid[s] + qrain[s]
+    qs = qice[s] + qsnow[s] + qgraupel[s]
+    gz = ql + qs
+    cv = (1.0 - (qvapor[s] + gz)) * CV_AIR + qvapor[s] * CV_VAP + ql * C_LIQ + qs * C_ICE
+    cvm[s] = cv
+    q_con[s] = gz
+    d1 = ZVIR * qvapor[s]
+    dp1[s] = d1
+    cp = RDGAS / (RDGAS + cv / (1.0 + d1))
+    cappa[s] = cp
+    pkz[s] = np.exp(cp * np.log(RDG * delp[s] * pt[s] * (1.0 + d1) * (1.0 - gz) / delz[s]))

@@ -490,7 +490,15 @@ def _fvsetup_expected(d):
     return d
 
 
-SPECS["fv_setup"] = StageSpec("fv_setup", "FVSetup#0", ("q_con", "cvm", "pkz", "cappa", "dp1", "pt"), _o_todo, _n_fvsetup, tol=1e-13,
+def _o_fvsetup(ix, g, a):
+    """The reference's fv_setup alone (pt is only adjusted by the next reference stencil, which the native call fuses)."""
+    from oracle import remap as O
+
+    O.fv_setup(a["qvapor"], a["qliquid"], a["qrain"], a["qsnow"], a["qice"], a["qgraupel"], a["q_con"], a["cvm"], a["pkz"],
+               a["pt"], a["cappa"], a["delp"], a["delz"], a["dp1"], ix.nx, ix.ny, ix.nz)
+
+
+SPECS["fv_setup"] = StageSpec("fv_setup", "FVSetup#0", ("q_con", "cvm", "pkz", "cappa", "dp1", "pt"), _o_fvsetup, _n_fvsetup, tol=1e-13,
                               case=S2, regions={n: COMPUTE for n in ("q_con", "cvm", "pkz", "cappa", "dp1", "pt")},
                               check_untouched=False, expected=_fvsetup_expected)
 
