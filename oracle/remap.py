@@ -259,3 +259,85 @@ def fv_setup(qvapor, qliquid, qrain, qsnow, qice, qgraupel, q_con, cvm, pkz, pt,
     cp = RDGAS / (RDGAS + cv / (1.0 + d1))
     cappa[s] = cp
     pkz[s] = np.exp(cp * np.log(RDG * delp[s] * pt[s] * (1.0 + d1) * (1.0 - gz) / delz[s]))
+
+
+def lagrangian_to_eulerian(a, nx, ny, nz, halo=3):
+    """LagrangianToEulerian.__call__ (remapping.py:485-695, do_sat_adj off, kord 9): init_pe (:42-50),
+    moist_cv_pt_pressure (:73-151), pn2_pk_delp (:154-166), map_single(pt) / mapn_tracer / fillz / map_single(w, delz),
+    undo_delz_adjust_and_copy_peln (:53-68), moist_pkz (moist_cv.py:112-141), pressures_mapu / _mapv (:196-254) with
+    map_single(u, v), update_ua + copy_from_below (:257-272), moist_pt_last_step / adjust_divide (:674-695).
+    `a` maps the argument names of the reference call to [i, j, k] arrays, updated in place."""
+    from .constants import C_ICE, C_LIQ, CV_AIR, CV_VAP, RDG, RDGAS
+
+    names = ["qvapor", "qliquid", "qrain", "qice", "qsnow", "qgraupel", "qo3mr", "qsgs_tke"]
+    tr = {n: a["tracers." + n] for n in names}
+    pt, delp, delz, peln, pe, pk, pkz = a["pt"], a["delp"], a["delz"], a["peln"], a["pe"], a["pk"], a["pkz"]
+    ak, bk = a["ak"], a["bk"]
+    ptop, akap, zvir = float(a["ptop"]), float(a["akap"]), float(a["zvir"])
+    ci, cj, cjp, cip = slice(halo, halo + nx), slice(halo, halo + ny), slice(halo, halo + ny + 1), slice(halo, halo + nx + 1)
+    K = slice(0, nz)
+
+    def moist_cv():
+        ql = tr["qliquid"][ci, cj, K] + tr["qrain"][ci, cj, K]
+        qs = tr["qice"][ci, cj, K] + tr["qsnow"][ci, cj, K] + tr["qgraupel"][ci, cj, K]
+        gz = ql + qs
+        qv = tr["qvapor"][ci, cj, K]
+        return (1.0 - (qv + gz)) * CV_AIR + qv * CV_VAP + ql * C_LIQ + qs * C_ICE, gz
+
+    pe1 = pe.copy()
+    pe2 = np.zeros_like(pe)
+    pe2[ci, cjp, 0] = ptop
+    pe2[ci, cjp, nz] = pe[ci, cjp, nz]
+    cvm, gz = moist_cv()
+    a["q_con"][ci, cj, K] = gz
+    cp = RDGAS / (RDGAS + cvm / (1.0 + zvir * tr["qvapor"][ci, cj, K]))
+    a["cappa"][ci, cj, K] = cp
+    pt[ci, cj, K] = pt[ci, cj, K] * np.exp(cp / (1.0 - cp) * np.log(RDG * delp[ci, cj, K] / delz[ci, cj, K] * pt[ci, cj, K]))
+    delz[ci, cj, K] = -delz[ci, cj, K] / delp[ci, cj, K]
+    psv = pe[ci, cj, nz].copy()
+    a["ps"][ci, cj] = psv
+    for k in range(1, nz):
+        pe2[ci, cj, k] = ak[k] + bk[k] * psv
+    dp2 = np.zeros_like(pe)
+    dp2[ci, cj, K] = pe2[ci, cj, 1 : nz + 1] - pe2[ci, cj, K]
+    delp[ci, cj, K] = dp2[ci, cj, K]
+    pn2 = np.zeros_like(pe)
+    pn2[ci, cj, nz] = peln[ci, cj, nz]
+    pn2[ci, cj, K] = np.log(pe2[ci, cj, K])
+    pk[ci, cj, K] = np.exp(akap * pn2[ci, cj, K])
+    map_single(pt, peln, pn2, None, 184.0, 1, nx, ny, nz)
+    for n in names:
+        map_single(tr[n], pe1, pe2, None, 0.0, 0, nx, ny, nz)
+    for n in names:
+        fillz(tr[n], dp2, nx, ny, nz)
+    map_single(a["w"], pe1, pe2, a["wsd"], 0.0, -2, nx, ny, nz)
+    map_single(delz, pe1, pe2, None, 0.0, 1, nx, ny, nz)
+    delz[ci, cj, K] = -delz[ci, cj, K] * delp[ci, cj, K]
+    peln[ci, cj, : nz + 1] = pn2[ci, cj, : nz + 1]
+    cvm, gz = moist_cv()
+    a["q_con"][ci, cj, K] = gz
+    cp = RDGAS / (RDGAS + cvm / (1.0 + zvir * tr["qvapor"][ci, cj, K]))
+    a["cappa"][ci, cj, K] = cp
+    pkz[ci, cj, K] = np.exp(cp * np.log(RDG * delp[ci, cj, K] / delz[ci, cj, K] * pt[ci, cj, K]))
+    # u on (nx, ny+1): pressures averaged across the y interface
+    pe0 = np.zeros_like(pe)
+    pe3 = np.zeros_like(pe)
+    pem = np.roll(pe, 1, axis=1)     # pe[i, j-1]
+    pe0[ci, cjp, 0] = pe[ci, cjp, 0]
+    pe0[ci, cjp, 1 : nz + 1] = 0.5 * (pem[ci, cjp, 1 : nz + 1] + pe[ci, cjp, 1 : nz + 1])
+    for k in range(nz + 1):
+        pe3[ci, cjp, k] = ak[k] + 0.5 * bk[k] * (pem[ci, cjp, nz] + pe[ci, cjp, nz])
+    map_single(a["u"], pe0, pe3, None, 0.0, -1, nx, ny, nz, j_extra=1)
+    pem = np.roll(pe, 1, axis=0)     # pe[i-1, j]
+    pe0[cip, cj, 0] = pe[cip, cj, 0]
+    pe0[cip, cj, 1 : nz + 1] = 0.5 * (pem[cip, cj, 1 : nz + 1] + pe[cip, cj, 1 : nz + 1])
+    pe3[cip, cj, 0] = ak[0]
+    for k in range(1, nz + 1):
+        pe3[cip, cj, k] = ak[k] + 0.5 * bk[k] * (pem[cip, cj, nz] + pe[cip, cj, nz])
+    map_single(a["v"], pe0, pe3, None, 0.0, -1, nx, ny, nz, i_extra=1)
+    pe[ci, cj, 1:nz] = pe2[ci, cj, 1:nz]
+    if bool(a["last_step"]):
+        gzl = tr["qliquid"][ci, cj, K] + tr["qrain"][ci, cj, K] + tr["qice"][ci, cj, K] + tr["qsnow"][ci, cj, K] + tr["qgraupel"][ci, cj, K]
+        pt[ci, cj, K] = (pt[ci, cj, K] + 0.0 * pkz[ci, cj, K]) / ((1.0 + zvir * tr["qvapor"][ci, cj, K]) * (1.0 - gzl))
+    else:
+        pt[ci, cj, K] = pt[ci, cj, K] / pkz[ci, cj, K]

@@ -514,8 +514,14 @@ def _n_remap(sf, qf, rt, q, d):
         bool(d["in.last_step"]), f(d, "consv_te"), f(d, "mdt"))
 
 
+def _o_remap(ix, g, a):
+    from oracle import remap as O
+
+    O.lagrangian_to_eulerian(a, ix.nx, ix.ny, ix.nz)
+
+
 _RM_OUT = ("pt", "delp", "delz", "peln", "u", "v", "w", "cappa", "q_con", "pkz", "pk", "pe", "ps", "tracers.qvapor")
 SPECS["remapping"] = StageSpec(
-    "remapping", "Remapping#0", _RM_OUT, _o_todo, _n_remap, tol=1e-11, near_zero=1e-13, case=S2, check_untouched=False,
+    "remapping", "Remapping#0", _RM_OUT, _o_remap, _n_remap, tol=1e-11, near_zero=1e-13, case=S2, check_untouched=False,
     tols={"w": 5e-6},
     regions={**{n: COMPUTE for n in _RM_OUT}, "u": _YI, "v": _XI})
