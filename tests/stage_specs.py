@@ -300,7 +300,15 @@ def _n_dzd(sf, qf, rt, q, d):
        q["ws"], f(d, "dt"))
 
 
-register(StageSpec("update_dz_d", "UpdateDzD#0", ("height", "ws"), _o_todo, _n_dzd, tol=1e-13,
+def _o_dzd(ix, g, a):
+    from oracle import updatedz as O
+
+    col = _columns()
+    O.update_dz_d(ix, g, a["surface_height"], a["height"], a["courant_number_x"], a["courant_number_y"], a["x_area_flux"],
+                  a["y_area_flux"], a["ws"], float(a["dt"]), col["damp_vt"], col["nord_v"], 6)
+
+
+register(StageSpec("update_dz_d", "UpdateDzD#0", ("height", "ws"), _o_dzd, _n_dzd, tol=1e-13,
                    regions={"height": COMPUTE, "ws": COMPUTE}, check_untouched=False))
 
 
