@@ -364,7 +364,13 @@ register(StageSpec("edge_pe", "PE_Halo#0", ("pe",), _o_edge_pe,
 register(StageSpec("pk3_halo", "PK3_Halo#0", ("pk3",), _o_pk3_halo,
                    lambda sf, qf, rt, q, d: rt.call("fv3_pk3_halo", q["pk3"].ptr, q["delp"].ptr, f(d, "ptop"), f(d, "akap")),
                    tol=1e-13, case=S2))
-register(StageSpec("nh_p_grad", "NH_P_Grad#0", ("u", "v", "pp", "gz", "pk3"), _o_todo,
+def _o_nhpg(ix, g, a):
+    from oracle import a2b as O
+
+    O.nh_p_grad(ix, g, a["u"], a["v"], a["pp"], a["gz"], a["pk3"], a["delp"], float(a["dt"]), float(a["ptop"]), float(a["akap"]))
+
+
+register(StageSpec("nh_p_grad", "NH_P_Grad#0", ("u", "v", "pp", "gz", "pk3"), _o_nhpg,
                    lambda sf, qf, rt, q, d: rt.call("fv3_nh_p_grad", q["u"].ptr, q["v"].ptr, q["pp"].ptr, q["gz"].ptr,
                                                     q["pk3"].ptr, q["delp"].ptr, f(d, "dt"), f(d, "ptop"), f(d, "akap")),
                    tol=1e-11, near_zero=1e-12, case=S2, check_untouched=False,
