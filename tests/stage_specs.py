@@ -265,7 +265,20 @@ def _n_divdamp(sf, qf, rt, q, d):
             cols.ref)
 
 
-register(StageSpec("divergence_damping", "DivergenceDamping#0", ("damped_rel_vort_bgrid", "ke", "delpc", "divg_d"), _o_todo,
+def _o_divdamp(ix, g, a):
+    from oracle import divergence_damping as O
+    from pace_b200.fv3core._config import baroclinic_config
+
+    col = _columns()
+    cfg = baroclinic_config(NX).d_grid_shallow_water
+    nord_col = np.asarray(col["nord"])
+    k0 = int(np.argmax(nord_col > 0)) if (nord_col > 0).any() else NZ
+    O.divergence_damping(ix, g, a["u"], a["v"], a["va"], a["damped_rel_vort_bgrid"], a["ua"], a["divg_d"], a["vc"], a["uc"],
+                         a["delpc"], a["ke"], a["rel_vort_agrid"], float(a["dt"]), np.asarray(col["d2_divg"]), k0,
+                         int(nord_col.max()), cfg.dddmp, cfg.d4_bg)
+
+
+register(StageSpec("divergence_damping", "DivergenceDamping#0", ("damped_rel_vort_bgrid", "ke", "delpc", "divg_d"), _o_divdamp,
                    _n_divdamp, regions={n: CORNERS for n in ("damped_rel_vort_bgrid", "ke", "delpc", "divg_d")}, tol=1e-13,
                    check_untouched=False))
 
