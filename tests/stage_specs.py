@@ -295,10 +295,17 @@ def _n_dsw(sf, qf, rt, q, d):
 
 _XI = (slice(3, 3 + NX + 1), slice(3, 3 + NX))      # x-interface fields on the compute rows
 _YI = (slice(3, 3 + NX), slice(3, 3 + NX + 1))
+def _o_dsw(ix, g, a):
+    from oracle import d_sw as O
+    from pace_b200.fv3core._config import baroclinic_config
+
+    O.d_sw(ix, g, a, _columns(), baroclinic_config(NX).d_grid_shallow_water)
+
+
 register(StageSpec(
     "d_sw", "D_SW#0",
     ("delp", "pt", "w", "q_con", "u", "v", "mfx", "mfy", "cx", "cy", "crx", "cry", "xfx", "yfx", "heat_source", "diss_est"),
-    _o_todo, _n_dsw, tol=1e-12, check_untouched=False,
+    _o_dsw, _n_dsw, tol=1e-12, check_untouched=False,
     regions={"delp": COMPUTE, "pt": COMPUTE, "w": COMPUTE, "q_con": COMPUTE, "u": _YI, "v": _XI, "mfx": _XI, "mfy": _YI,
              "cx": _XI, "cy": _YI, "crx": (slice(3, 3 + NX + 1), slice(None)), "cry": (slice(None), slice(3, 3 + NX + 1)),
              "xfx": (slice(3, 3 + NX + 1), slice(None)), "yfx": (slice(None), slice(3, 3 + NX + 1)),
