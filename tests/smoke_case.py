@@ -22,3 +22,20 @@ def run(verbose=False):
     H.assert_close(q["pef"].numpy()[0], pef, 1e-12, name="pef")
     if verbose:
         print("riem_solver_c: CUDA == oracle within 1e-12")
+    # the hottest stage and the vertical remap, same way: native call vs the numpy restatement on the committed inputs
+    from oracle.indexing import Idx
+    from tests.stage_specs import NX, NZ, SPECS
+    from tests.test_stages import _grid, run_native
+
+    for name in ("d_sw@s2", "remapping"):
+        spec = SPECS[name]
+        d = H.load_stage(spec.case, 0, spec.golden)
+        q = run_native(spec, d)
+        a = {k[3:]: v.copy() for k, v in d.items() if k.startswith("in.")}
+        spec.oracle(Idx(NX, NX, NZ), _grid(spec.case), a)
+        for n in spec.outputs:
+            reg = spec.regions.get(n, (slice(None), slice(None)))
+            H.assert_close(q[n].numpy()[0][reg], a[n][reg], max(spec.tols.get(n, spec.tol), 1e-11), max(spec.near_zero, 1e-13),
+                           name=f"{name}.{n}")
+        if verbose:
+            print(f"{name}: CUDA == oracle")
