@@ -27,15 +27,23 @@ def main():
     ap.add_argument("--n-split", type=int, default=1)
     ap.add_argument("--k-split", type=int, default=1)
     ap.add_argument("--capture-step", type=int, default=0, help="0-based index of the step whose stages are captured")
+    ap.add_argument("--fill-tracers", action="store_true",
+                    help="BASELINE configs[3]: tracer m (1..7) = qvapor * (m + 1) / 10 before the first step (SURVEY.md §8d)")
+    ap.add_argument("--stages", nargs="*", default=None, help="capture only these stages (default: all)")
+    ap.add_argument("--do-sat-adj", action="store_true", help="the stock baroclinic_c12.yaml setting (row f1)")
     args = ap.parse_args()
 
     from oracle.refshim import runner
 
     os.makedirs(args.out, exist_ok=True)
     t0 = time.time()
+    overrides = dict(n_split=args.n_split, k_split=args.k_split)
+    if args.do_sat_adj:
+        overrides["do_sat_adj"] = True
     ctxs, cap = runner.run(
         args.nx, (args.layout, args.layout), nsteps=args.nsteps, capture_ranks=tuple(args.capture_ranks),
-        config_overrides=dict(n_split=args.n_split, k_split=args.k_split), capture_step=args.capture_step,
+        config_overrides=overrides, capture_step=args.capture_step, stages=args.stages,
+        on_built=runner.fill_tracers if args.fill_tracers else None,
     )
     for ctx in ctxs:
         r = ctx["rank"]
@@ -50,7 +58,7 @@ def main():
             flat.update({f"out.{k}": v for k, v in rec["out"].items()})
             np.savez(os.path.join(d, key + ".npz"), **flat)
     meta = dict(capture_step=args.capture_step, nx=args.nx, layout=args.layout, nsteps=args.nsteps, n_split=args.n_split, k_split=args.k_split,
-                timing=ctxs[0].get("timing"), wall=time.time() - t0, config=runner.C12_CONFIG,
+                fill_tracers=bool(args.fill_tracers), do_sat_adj=bool(args.do_sat_adj), timing=ctxs[0].get("timing"), wall=time.time() - t0, config=runner.C12_CONFIG,
                 reference="ai2cm/pace @ /root/reference, numpy backend via oracle/refshim")
     with open(os.path.join(args.out, "meta.json"), "w") as f:
         json.dump(meta, f, indent=1, default=str)

@@ -310,6 +310,18 @@ def state_arrays(state):
     return out
 
 
+TRACERS = ("qvapor", "qliquid", "qrain", "qice", "qsnow", "qgraupel", "qo3mr", "qsgs_tke")
+
+
+def fill_tracers(ctx, scale=0.1):
+    """BASELINE configs[3]: all 8 advected tracers non-trivial, q_m = qvapor * (m + 1) / 10 — the
+    same rule as pace_b200.fv3core.initialization.baroclinic.fill_tracers, applied to the reference's own state."""
+    st = ctx["state"]
+    qv = np.array(st.qvapor.data, copy=True)
+    for m, name in enumerate(TRACERS[1:], start=1):
+        getattr(st, name).data[:] = qv * (m + 1) * scale
+
+
 def run(nx, layout=(1, 1), nsteps=1, capture_ranks=(0,), stages=None, config_overrides=None, build_only=False,
         on_built=None, verbose=True, capture_step=0):
     """Run `nsteps` of the reference dycore on 6*layout^2 thread-ranks.
