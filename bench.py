@@ -102,51 +102,63 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_port_seconds_per_step(nx_sample, layout, k_split, n_split, steps, warmup, nx_target, verbose=False):
-    """The CPU port (host simulation of the same stage functors, OpenMP over all host cores; oracle/hostsim.py) timed on
-    a bounded sample of the workload and scaled by the cell-count ratio to the target resolution."""
+def cpu_port_run(nx, layout, k_split, n_split, steps, warmup, budget_s=None):
+    """The CPU port (host simulation of the same stage functors, OpenMP over the host cores; oracle/hostsim.py) on the
+    C`nx` workload: (mean seconds per step, measured steps, threads actually used).  With `budget_s` the number of
+    measured steps is cut (never below 1) so that the whole run fits the budget."""
     import torch
 
     from oracle import hostsim
 
-    hostsim.install(openmp=True)
-    dycore, state, comm, rt, gd = build_dycore(nx_sample, layout, 79, k_split, n_split, "cpu")
-    for _ in range(warmup):
+    cores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(cores)   # unconditional: torchrun exports OMP_NUM_THREADS=1
+    lib = hostsim.install(openmp=True, threads=cores)
+    threads = hostsim.threads_in_use(lib)
+    dycore, state, comm, rt, gd = build_dycore(nx, layout, 79, k_split, n_split, "cpu")
+    t0 = time.perf_counter()
+    dycore.step_dynamics(state)          # first step: also the calibration of the budget
+    t_first = time.perf_counter() - t0
+    n_warm = max(warmup - 1, 0)
+    if budget_s is not None:
+        room = max(int(budget_s / max(t_first, 1e-3)) - 1, 1)
+        n_warm = min(n_warm, max(room - steps, 0))
+        steps = max(min(steps, room - n_warm), 1)
+    for _ in range(n_warm):
         dycore.step_dynamics(state)
     t0 = time.perf_counter()
     for _ in range(steps):
         dycore.step_dynamics(state)
     dt = (time.perf_counter() - t0) / steps
     assert bool(torch.isfinite(state.pt.data[:, 3:-4, 3:-4, :79]).all()), "CPU port produced non-finite values"
-    return dt * (nx_target / nx_sample) ** 2, dt
+    return dt, steps, n_warm + 1, threads
+
+
+def reference_numpy_note():
+    """The reference's OWN numpy backend cannot run on the GPU box (Python + vendored GT4Py, /root/reference is not
+    shipped); its measured cost in the build container is recorded by oracle/refshim/time_reference.py in
+    profiles/reference_numpy_timing.json and repeated here for orientation."""
+    p = os.path.join(ROOT, "profiles", "reference_numpy_timing.json")
+    return json.load(open(p)) if os.path.exists(p) else None
 
 
 def run_reference_arm(args):
     """`--impl reference`: the CPU implementation of the path on the host cores.  The reference itself is Python + a
     GT4Py tool-chain that is neither installable nor present on the GPU box, so this arm times the CPU port
-    (oracle/hostsim.py), as the tier contract prescribes when the reference cannot be compiled."""
+    (oracle/hostsim.py: this repo's stage functors compiled for the host, OpenMP) — `kind: "port"`, NOT a measurement
+    of the reference's code — on the SAME workload (C128 by default), a bounded number of steps."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-    total = args.steps + args.warmup
-    # calibrate on c24 and pick the largest sample that keeps the whole run within ~4 minutes
-    scaled, t24 = cpu_port_seconds_per_step(24, args.layout, args.k_split, args.n_split, 1, 0, args.nx)
-    nx_sample = 24
-    for cand in (48, 32):
-        if t24 * (cand / 24) ** 2 * total < 200.0:
-            nx_sample = cand
-            break
-    value, raw = cpu_port_seconds_per_step(nx_sample, args.layout, args.k_split, args.n_split, args.steps, args.warmup, args.nx)
-    sample = (f"C{nx_sample} L79 layout ({args.layout},{args.layout}) full timestep (k_split={args.k_split}, n_split={args.n_split}), "
-              f"{raw:.3f} s/step measured, scaled by cell count x{(args.nx / nx_sample) ** 2:.2f} to C{args.nx}")
+    value, steps, warm, threads = cpu_port_run(args.nx, args.layout, args.k_split, args.n_split, args.steps, args.warmup, budget_s=240.0)
+    sample = (f"C{args.nx} L79 layout ({args.layout},{args.layout}) full timestep (k_split={args.k_split}, n_split={args.n_split}), the workload "
+              f"itself: mean of {steps} step(s) after {warm} warm-up step(s) on {threads} OpenMP threads (steps cut to a 240 s budget)")
     line = {
         "impl": "reference", "metric": "C128L79 baroclinic dycore s/timestep", "value": value, "unit": "s/timestep",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": value * 1e3,
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": value * 1e3,
         "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args),
-        "cpu_baseline": {"value": value, "unit": "s/timestep", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "s/timestep", "cores": threads, "kind": "port", "sample": sample,
+                         "reference_numpy": reference_numpy_note()},
         "e2e": {"value": value, "unit": "s/timestep", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -372,16 +384,15 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        cores = os.cpu_count() or 1
-        os.environ.setdefault("OMP_NUM_THREADS", str(cores))
         _prod = _lib._lib
         try:
-            scaled, raw = cpu_port_seconds_per_step(24, args.layout, args.k_split, args.n_split, 1, 1, args.nx)
+            dt, n_meas, n_warm, threads = cpu_port_run(args.nx, args.layout, args.k_split, args.n_split, 1, 1, budget_s=30.0)
         finally:
             _lib.install(_prod)   # back to the CUDA library
-        cpu = {"value": scaled, "unit": "s/timestep", "cores": cores, "kind": "port",
-               "sample": f"c24 L79 layout ({args.layout},{args.layout}) full timestep (same k_split/n_split), {raw:.3f} s/step measured after 1 warm-up, "
-                         f"scaled by cell count x{(args.nx / 24) ** 2:.2f} to C{args.nx}"}
+        cpu = {"value": dt, "unit": "s/timestep", "cores": threads, "kind": "port",
+               "sample": f"C{args.nx} L79 layout ({args.layout},{args.layout}) full timestep (same k_split/n_split), the workload itself: "
+                         f"{n_meas} step after {n_warm} warm-up on {threads} OpenMP threads",
+               "reference_numpy": reference_numpy_note()}
 
     line = {
         "metric": "C128L79 baroclinic dycore s/timestep", "value": ms / 1e3, "unit": "s/timestep", "n_gpus": world,

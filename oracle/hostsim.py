@@ -54,10 +54,22 @@ def load(openmp=False, build_if_missing=True):
     return lib
 
 
-def install(openmp=False):
-    """Make pace_b200 run on the host simulation in THIS process (tests / CPU baseline only)."""
+def install(openmp=False, threads=None):
+    """Make pace_b200 run on the host simulation in THIS process (tests / CPU baseline only).  `threads`: OpenMP
+    thread count set EXPLICITLY through the runtime (an inherited OMP_NUM_THREADS=1, as torchrun exports, would
+    otherwise pin the port to one core)."""
     from pace_b200 import _lib
 
     lib = load(openmp)
+    if openmp and threads:
+        lib.omp_set_num_threads(int(threads))
     _lib.install(lib)
     return lib
+
+
+def threads_in_use(lib):
+    """OpenMP threads the host-simulation library will actually use (1 for the serial build)."""
+    try:
+        return int(lib.omp_get_max_threads())
+    except AttributeError:
+        return 1

@@ -128,7 +128,8 @@ FV_DEV void a2b_plane(const fv3_geom &g, const fv3_grid &m, int s, const B &b, c
   b.rect(0, nwi, b.lo(0, h), b.hi(nwj, h), [&](int i, int j) { SQ[j * sj + i] = qin[j * sj + i]; });
   auto q = [&](int ii, int jj) { return SQ[jj * sj + ii]; };
   // qx on corner columns isc..iec+1, rows ja-2..jb+1; qy on rows ja..jb, columns isc-2..iec+2
-  const int xj0 = b.lo(jsc - 2, 2), xj1 = b.hi(jec + 3, 2), yj0 = ja, yj1 = jb + 1;
+  // (a last strip of ONE row on a north tile edge: its row jec reads qx three rows down, a2b_ord4.py:286-311)
+  const int xj0 = b.lo(jsc - 2, (N && jb - ja < 2) ? 3 : 2), xj1 = b.hi(jec + 3, 2), yj0 = ja, yj1 = jb + 1;
   const int nxc = g.nx + 1, nxw = g.nx + 4, nxr = xj1 - xj0, nyr = yj1 - yj0;
   // The two columns (rows) either side of a tile edge use the one-sided formulas (divides, metric loads): they are
   // separate, densely packed tasks of the same phase instead of a few slow lanes in every warp of the bulk pass.

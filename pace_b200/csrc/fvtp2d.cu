@@ -432,6 +432,7 @@ int fv3_tracer_subcycle(fv3_ctx *ctx, double *const *tracers, int nq, double *dp
     const int h = g.halo, R = sg.rows_per_strip;
     fv3::launch3d(ctx, (cudaStream_t)stream, h, h + g.nx, 0, 2 * h * (sg.ns - 1), 0, g.nz, FV_LAMBDA(int s, int i, int jj, int k) { FV_DEV_GM
       const int h2 = g.halo, bnd = jj / (2 * h2), j = h2 + (bnd + 1) * R - h2 + (jj - bnd * 2 * h2);
+      if (j >= h2 + g.ny) return;  // a last strip shorter than the halo: rows beyond the compute domain were never parked
       const int64_t o = O3(s, i, j, k);
       for (int n = 0; n < nq; ++n) tracers[n][o] = side0[n * side_stride + o];
     });

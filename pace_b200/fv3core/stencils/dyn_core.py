@@ -144,10 +144,9 @@ class AcousticDynamics:
         """zero_data (dyn_core.py:48-80)"""
         for q in (state.mfxd, state.mfyd, state.cxd, state.cyd):
             q.data.zero_()
-        if first_timestep:
-            h = self._rt.comm.geometry.halo
-            self._heat_source.data[:, h:-h, h:-h, :].zero_()
-            state.diss_estd.data[:, h:-h, h:-h, :].zero_()
+        if first_timestep:  # domain_full, as the reference
+            self._heat_source.data.zero_()
+            state.diss_estd.data.zero_()
 
     def __call__(self, state, timestep: float, n_map=1):
         rt, cfg, hu = self._rt, self.config, self._halo_updaters

@@ -76,6 +76,8 @@ class DynamicalCore:
         self._c2l_updater = comm.get_vector_halo_updater([qf.get_quantity_halo_spec(_U3)], [qf.get_quantity_halo_spec(_V3)])
         names6 = ["qvapor", "qliquid", "qrain", "qsnow", "qice", "qgraupel"]
         self._t6 = torch.tensor([getattr(state, n).ptr for n in names6], dtype=torch.int64).to(rt.device)
+        self._bound_state = state
+        self._bound_ptrs = {n: getattr(state, n).ptr for n in list(TRACER_VARIABLES[:NQ]) + ["u", "v", "w", "delp", "pt", "delz", "q_con"]}
         self._n_split, self._k_split = config.n_split, config.k_split
         self._timestep = timestep.total_seconds()
 
@@ -84,7 +86,19 @@ class DynamicalCore:
             self.checkpointer(f"FVDynamics-{tag}", u=state.u, v=state.v, w=state.w, delz=state.delz, va=state.va,
                               uc=state.uc, vc=state.vc, qvapor=state.qvapor)
 
+    def _check_bound_state(self, state):
+        """The tracer pointer table, the tracer dictionary and every halo updater are bound to the DycoreState given at
+        construction (the reference binds its halo updaters the same way, dyn_core.py:273-343).  A different state
+        object must not silently advance with the construction-time tracers."""
+        if state is self._bound_state:
+            return
+        for n in self._bound_ptrs:
+            if getattr(state, n).ptr != self._bound_ptrs[n]:
+                raise ValueError(f"step_dynamics: state.{n} is not the buffer this DynamicalCore was constructed with; "
+                                 "the halo updaters and tracer tables are bound at construction")
+
     def step_dynamics(self, state: DycoreState, timer=NullTimer()):
+        self._check_bound_state(state)
         self._checkpoint_fvdynamics(state, "In")
         self._compute(state, timer)
         self._checkpoint_fvdynamics(state, "Out")

@@ -69,3 +69,41 @@ def test_c48_strip_count_does_not_change_a_bit(device):
         pytest.skip("host simulation is exercised on CPU-only boxes")
     auto, one, five = _c48_digest(0), _c48_digest(1), _c48_digest(5)
     assert auto == one == five
+
+
+_SMALL_SCRIPT = r"""
+import hashlib, sys
+from datetime import timedelta
+import numpy as np
+sys.path.insert(0, %r)
+from oracle import hostsim
+hostsim.install(openmp=True)
+import bench
+dycore, state, comm, rt, gd = bench.build_dycore(%d, 1, 79, 1, 2, "cpu", all_tracers=True)
+dycore.step_dynamics(state)
+out = state.as_numpy()
+h = hashlib.sha1()
+for n in ("u", "v", "w", "delp", "pt", "delz", "qvapor", "qliquid", "qsgs_tke"):
+    h.update(np.ascontiguousarray(out[n]).tobytes())
+print("DIGEST", h.hexdigest())
+"""
+
+
+def _small_digest(nx, n_strips):
+    env = dict(os.environ)
+    env.pop("FV3_FORCE_STRIPS", None)
+    if n_strips:
+        env["FV3_FORCE_STRIPS"] = str(n_strips)
+    r = subprocess.run([sys.executable, "-c", _SMALL_SCRIPT % (ROOT, nx)], cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return [l for l in r.stdout.splitlines() if l.startswith("DIGEST")][0]
+
+
+@pytest.mark.parametrize("nx,n_strips", [(13, 4), (17, 4)])
+def test_last_strip_shorter_than_the_halo(device, nx, n_strips):
+    """ny % rows_per_strip in {1, 2}: c13 in 4 strips = 4 + 4 + 4 + 1 rows, c17 in 4 strips = 5 + 5 + 5 + 2 rows: the in-place
+    tracer update parks the rows a neighbouring strip reads as halo and copies them back afterwards; rows beyond the
+    compute domain were never parked and must not be copied (8 non-zero tracers, two substeps, one timestep)."""
+    if device != "cpu":
+        pytest.skip("host simulation is exercised on CPU-only boxes")
+    assert _small_digest(nx, 1) == _small_digest(nx, n_strips)
