@@ -48,6 +48,13 @@ def load(case):
     nranks = 6 * meta["layout"] ** 2
     grids = [dict(np.load(os.path.join(inp, f"grid_rank{r}.npz"))) for r in range(nranks)]
     s0 = [dict(np.load(os.path.join(inp, f"state0_rank{r}.npz"))) for r in range(nranks)]
+    from pace_b200.fv3core.dycore_state import FIELDS
+
+    for z in s0:  # fields absent from a reduced input dump are identically zero
+        shape3 = z["delp"].shape
+        for n, (dims, _) in FIELDS.items():
+            if n not in z:
+                z[n] = np.zeros(shape3 if len(dims) == 3 else shape3[:2])
     if meta.get("fill_tracers"):
         for z in s0:
             for m, n in enumerate(TRACERS[1:], start=1):
