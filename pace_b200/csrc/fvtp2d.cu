@@ -47,11 +47,18 @@ FV_DEV void fvtp2d_plane(const fv3_geom &g, const fv3_grid &m, int s, int k, con
     if (a.xu != a.xfx) b.prefetch_rows(a.xu + ob, sj);
     if (a.yu != a.yfx) b.prefetch_rows(a.yu + ob, sj);
   }
-  // 1. load q; 3x3 cube-corner halo blocks as copy_corners_y leaves them
-  b.rect(0, nwi, rl, rh, [&](int i, int j) {
+  // 1. load q: the strip's resident rows are one contiguous range of the global plane -> ONE bulk (TMA) copy; then the
+  //    3x3 cube-corner halo blocks as copy_corners_y leaves them
+  b.bulk_begin(1, sj);
+  b.bulk_rows(Q, q, sj);
+  b.bulk_wait();
+  b.par(4 * h * h, [&](int t) {
+    const int c = t / (h * h), r = t - c * h * h, a1 = r / h, b1 = r - a1 * h;
+    const int i = (c & 1) ? iec + 1 + a1 : a1, j = (c & 2) ? jec + 1 + b1 : b1;
+    if (j < rl || j >= rh) return;
     int ii = i, jj = j;
-    if ((i < isc || i > iec) && (j < jsc || j > jec)) fv3::corner_y(g, s, ii, jj);
-    Q[j * sj + i] = FV_LDG(q + jj * sj + ii);
+    fv3::corner_y(g, s, ii, jj);
+    if (ii != i || jj != j) Q[j * sj + i] = q[jj * sj + ii];
   });
   // 2. inner y sweep on q: all columns, faces ja .. jb
   fv3::ppm_sweep<MORD, false>(b, Q, sj, cry, dya, ey, 0, nwi, ja, jb, rl, rh, [&](int p, double val) { A[p] = val; });

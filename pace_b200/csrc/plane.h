@@ -30,7 +30,10 @@ struct Block {
   int ja, jb;   // owned rows: results on cell rows [ja, jb), y-faces / corner rows [ja, jb]
   int r0, r1;   // resident rows [r0, r1)
   bool last;    // jb is the top of the compute domain (this strip also stores face / corner row jb)
+  bool first;   // ja is the bottom of the compute domain
   int s_next, r0_next, nrows_next;  // the (subdomain, strip rows) a CTA of the NEXT wave will start on; s_next < 0: none
+  unsigned long long *bar;  // mbarrier of the bulk (TMA) plane loads (device only)
+  mutable unsigned phase;   // its current phase parity
 
   FV_HD double *plane(int n) const { return sm + (int64_t)n * pl - off; }
   FV_HD int jtop() const { return last ? jb : jb - 1; }  // last face / corner row this strip stores
@@ -78,6 +81,49 @@ struct Block {
   FV_DEV void rect(int i0, int i1, int j0, int j1, F f) const {
     par2(i1 > i0 ? i1 - i0 : 0, j1 > j0 ? j1 - j0 : 0, [&](int ir, int jr) { f(i0 + ir, j0 + jr); });
   }
+  // ---- asynchronous plane staging: the resident rows [r0, r1) of a global (s, k) plane are ONE contiguous range, so a
+  // whole strip of a field is moved HBM/L2 -> shared memory by a single cp.async.bulk (TMA, no register staging, no
+  // per-point address arithmetic); completion is signalled on the CTA's mbarrier.
+  //   bulk_begin(n)           one thread arms the barrier for n planes          (block-uniform call)
+  //   bulk_rows(dst, plane0)  one thread issues the copy of rows [r0, r1) of the global plane into the shared plane
+  //   bulk_wait()             everybody waits for the bytes to land
+  FV_HD int bulk_doubles(int sj) const { return (r1 - r0) * sj; }
+#ifdef FV3_HOSTSIM
+  void bulk_begin(int, int) const {}
+  void bulk_rows(double *dst, const double *plane0, int sj) const {
+    for (int t = r0 * sj; t < r1 * sj; ++t) dst[t] = plane0[t];
+  }
+  void bulk_wait() const {}
+#else
+  __device__ __forceinline__ void bulk_begin(int n_planes, int sj) const {
+    __syncthreads();  // every earlier (generic-proxy) access of the destination planes is done
+    if (threadIdx.x == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(n_planes * bulk_doubles(sj) * 8) : "memory");
+    }
+  }
+  __device__ __forceinline__ void bulk_rows(double *dst, const double *plane0, int sj) const {
+    if (threadIdx.x == 0) {
+      const unsigned d = (unsigned)__cvta_generic_to_shared(dst + r0 * sj), a = (unsigned)__cvta_generic_to_shared(bar);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d),
+                   "l"(plane0 + r0 * sj), "r"(bulk_doubles(sj) * 8), "r"(a)
+                   : "memory");
+    }
+  }
+  __device__ __forceinline__ void bulk_wait() const {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(a), "r"(phase)
+          : "memory");
+    }
+    phase ^= 1u;
+  }
+#endif
   // resident rows of the global plane starting at `plane0`
   FV_DEV void prefetch_rows(const double *plane0, int sj) const { prefetch_l2(plane0 + r0 * sj, (r1 - r0) * sj); }
   // First-touch operand of a CTA one wave ahead (same level, `field` = start of the 3-D field): its HBM -> L2 transfer
@@ -128,6 +174,9 @@ FV_HD Block make_block(const fv3_geom &g, double *sm, int strip, int rows_per_st
   b.ja = jsc + strip * rows_per_strip;
   b.jb = b.ja + rows_per_strip < jend ? b.ja + rows_per_strip : jend;
   b.last = b.jb == jend;
+  b.first = strip == 0;
+  b.bar = nullptr;
+  b.phase = 0;
   b.r0 = b.ja - g.halo;
   b.r1 = b.jb + g.halo + 1 < g.nj ? b.jb + g.halo + 1 : g.nj;
   b.pl = res_rows * g.sj;
@@ -138,8 +187,15 @@ FV_HD Block make_block(const fv3_geom &g, double *sm, int strip, int rows_per_st
 #ifndef FV3_HOSTSIM
 template <class F>
 __global__ void __launch_bounds__(PLANE_THREADS, 2) kplane(F f, int k0, int rows_per_strip, int res_rows, int ahead) {
-  extern __shared__ double plane_smem[];
+  extern __shared__ __align__(128) double plane_smem[];
+  __shared__ unsigned long long plane_bar;
   Block b = make_block(c_g, plane_smem, (int)blockIdx.z, rows_per_strip, res_rows);
+  b.bar = &plane_bar;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&plane_bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
   {  // blocks are dispatched level-fastest, then subdomain, then strip: `ahead` subdomains later = one wave later
     int sn = (int)blockIdx.y + ahead, zn = (int)blockIdx.z;
     if (sn >= (int)gridDim.y) {
