@@ -61,7 +61,7 @@ FV_DEV void fvtp2d_plane(const fv3_geom &g, const fv3_grid &m, int s, int k, con
     if (ii != i || jj != j) Q[j * sj + i] = q[jj * sj + ii];
   });
   // 2. inner y sweep on q: all columns, faces ja .. jb
-  fv3::ppm_sweep<MORD, false>(b, Q, sj, cry, dya, ey, 0, nwi, ja, jb, rl, rh, [&](int p, double val) { A[p] = val; });
+  fv3::ppm_sweep<MORD, false>(b, Q, sj, cry, dya, ey, 0, nwi, ja, jb, [&](int p, double val) { A[p] = val; });
   // 3. cube-corner blocks as copy_corners_x leaves them
   b.par(4 * h * h, [&](int t) {
     const int c = t / (h * h), r = t - c * h * h, a1 = r / h, b1 = r - a1 * h;
@@ -72,7 +72,7 @@ FV_DEV void fvtp2d_plane(const fv3_geom &g, const fv3_grid &m, int s, int k, con
     Q[j * sj + i] = q[jj * sj + ii];
   });
   // 4. inner x sweep on q: resident rows, faces isc .. iec+1
-  fv3::ppm_sweep<MORD, true>(b, Q, sj, crx, dxa, ex, rl, rh - rl, isc, iec + 1, 0, sj, [&](int p, double val) { B[p] = val; });
+  fv3::ppm_sweep<MORD, true>(b, Q, sj, crx, dxa, ex, rl, rh - rl, isc, iec + 1, [&](int p, double val) { B[p] = val; });
   // 5. transverse updates: q_i (into Q, owned rows) and q_j (into D, compute columns of the resident rows)
   b.rect(0, nwi, rl, rh, [&](int i, int j) {
     const int p = j * sj + i;
@@ -90,10 +90,10 @@ FV_DEV void fvtp2d_plane(const fv3_geom &g, const fv3_grid &m, int s, int k, con
   });
   // 6. outer x sweep on q_i (owned rows) -> x flux, in place over fx_in
   const double *xu = a.xu + ob, *yu = a.yu + ob;
-  fv3::ppm_sweep<MORD, true>(b, Q, sj, crx, dxa, ex, ja, jb - ja, isc, iec + 1, 0, sj,
+  fv3::ppm_sweep<MORD, true>(b, Q, sj, crx, dxa, ex, ja, jb - ja, isc, iec + 1,
                              [&](int p, double val) { B[p] = 0.5 * (val + B[p]) * FV_LDG(xu + p); });
   // 7. outer y sweep on q_j (compute columns) -> y flux, in place over fy_in
-  fv3::ppm_sweep<MORD, false>(b, D, sj, cry, dya, ey, isc, nx, ja, jb, rl, rh,
+  fv3::ppm_sweep<MORD, false>(b, D, sj, cry, dya, ey, isc, nx, ja, jb,
                               [&](int p, double val) { A[p] = 0.5 * (val + A[p]) * FV_LDG(yu + p); });
 }
 

@@ -22,6 +22,10 @@
 namespace fv3 {
 
 constexpr int PLANE_THREADS = 512;
+// guard doubles before the first / after the last shared plane: the register-window loads of the PPM sweeps (sweep.h)
+// run unconditionally and may reach 4 doubles before a row and 2 rows beyond the resident range (never used, never stored)
+constexpr int PLANE_PAD_FRONT = 16;
+FV_HD int plane_pad_back(int sj) { return 2 * sj + 16; }
 constexpr int PLANE_SMEM_BUDGET = (233472 / 2) - 1024;  // bytes per CTA for two CTAs per SM (228 KB, 1 KB reserved each)
 
 struct Block {
@@ -148,7 +152,7 @@ inline StripGeom strip_geometry(const fv3_geom &g, int n_planes) {
   for (int ns = forced > 0 ? forced : 1; ns <= g.ny; ++ns) {
     const int r = (g.ny + ns - 1) / ns, res = (r + 2 * g.halo + 1 < g.nj) ? r + 2 * g.halo + 1 : g.nj;
     if (r < 4) break;
-    const int64_t bytes = (int64_t)n_planes * res * g.sj * 8;
+    const int64_t bytes = ((int64_t)n_planes * res * g.sj + PLANE_PAD_FRONT + plane_pad_back(g.sj)) * 8;
     if (forced > 0 || bytes <= PLANE_SMEM_BUDGET) {
       sg = StripGeom{(g.ny + r - 1) / r, r, res};
       break;
@@ -169,7 +173,7 @@ FV_HD Block make_block(const fv3_geom &g, double *sm, int strip, int rows_per_st
   Block b;
   b.s_next = -1;
   b.r0_next = b.nrows_next = 0;
-  b.sm = sm;
+  b.sm = sm + PLANE_PAD_FRONT;
   const int jsc = g.halo, jend = g.halo + g.ny;
   b.ja = jsc + strip * rows_per_strip;
   b.jb = b.ja + rows_per_strip < jend ? b.ja + rows_per_strip : jend;
@@ -222,7 +226,7 @@ inline int launch_planes(const fv3_ctx *ctx, cudaStream_t st, int k0, int k1, in
     set_error("launch_planes: no strip decomposition of the plane fits in shared memory");
     return -1;
   }
-  const size_t doubles = (size_t)n_planes * sg.res_rows * ctx->g.sj;
+  const size_t doubles = (size_t)n_planes * sg.res_rows * ctx->g.sj + PLANE_PAD_FRONT + plane_pad_back(ctx->g.sj);
 #ifdef FV3_HOSTSIM
   (void)st;
   const int n_sub = ctx->g.n_sub;

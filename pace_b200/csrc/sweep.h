@@ -64,25 +64,47 @@ FV_HD double ppm_face_8(double c, bool pos, double qm, double q0, double qq, dou
   return pos ? q0 + (1.0 - c) * (br - c * b0) : q0 + (1.0 + c) * (bl + c * b0);
 }
 
+// Generic evaluation of ONE face next to a tile edge (any hord): out of line, one copy per kernel — it is executed by
+// a few lanes of tile-edge CTAs only and its one-sided formulas (divides, min / max clamps) are long.
+template <int MORD>
+#ifndef FV3_HOSTSIM
+__device__ __noinline__
+#else
+inline
+#endif
+    double
+    ppm_edge_face(const double *ql, const double *dl, int st, double c, int f, Edge1D e) {
+  auto q = [&](int ii) { return ql[ii * st]; };
+  auto dx = [&](int ii) { return dl[ii * st]; };
+  if (MORD < 8) {
+    auto al = [&](int ii) { return ppm_al_lt8(q, dx, ii, e); };
+    return ppm_flux_staged<MORD>(q, al, dx, c, f, e);
+  }
+  auto dm = [&](int ii) { return ppm_dm8(q, ii); };
+  return ppm_flux_staged<8>(q, dm, dx, c, f, e);
+}
+
 // Qs: values (shared plane).  XDIR: sweep along i (stride 1) on lines j in [l0, l0+nl), else along j (stride sj) on
 // lines i in [l0, l0+nl).  cg: Courant numbers, dxg: cell widths (global planes, same offsets).  Interface values are
-// produced for the faces [f0, f1] of every line (the whole line: e.start .. e.end + 1; a strip sweeping along j passes
-// its own face rows).  [v0, v1): indices along the sweep direction that may be READ from Qs (resident rows for a y
-// sweep; the padded row for an x sweep) — window loads outside it are skipped, their faces are never stored.
+// produced for the faces [f0, f1] of every line, e.start <= f0, f1 <= e.end + 1 (the whole line; a strip sweeping along j
+// passes its own face rows).
 // fin(p, value): what to do with the value at plane offset p; it must not write Qs.
 template <int MORD, bool XDIR, class Fin>
 FV_DEV void ppm_sweep(const Block &b, const double *Qs, int sj, const double *cg, const double *dxg, const Edge1D &e,
-                      int l0, int nl, int f0, int f1, int v0, int v1, Fin fin) {
+                      int l0, int nl, int f0, int f1, Fin fin) {
   constexpr int R = SWEEP_R;
   const int st = XDIR ? 1 : sj, ls = XDIR ? sj : 1;
   if (nl <= 0 || f1 < f0) return;  // uniform over the block
   // faces the edge tasks own (skipped by the bulk tasks); empty ranges away from tile edges
   const int elo0 = e.start, elo1 = e.lo ? e.start + 2 : e.start - 1;  // [elo0, elo1]
   const int ehi0 = e.hi ? e.end - 1 : e.end + 2, ehi1 = e.end + 1;    // [ehi0, ehi1]
+  // faces the bulk tasks store: [f0, f1] minus the edge faces (contiguous with the ends of the line)
+  const int fv0 = (e.lo && f0 <= elo1) ? elo1 + 1 : f0, fv1 = (e.hi && f1 >= ehi0) ? ehi0 - 1 : f1;
+  const unsigned nfv = fv1 >= fv0 ? (unsigned)(fv1 - fv0) : 0u;
   // x sweeps: groups start at multiples of R so that the 128-bit window loads are aligned
-  const int fb = XDIR ? (f0 & ~(R - 1)) : f0;
-  const int ng = (f1 - fb) / R + 1;
-  const int nbulk = ng * nl, nedge = (e.lo || e.hi) ? 6 * nl : 0;
+  const int fb = XDIR ? (fv0 & ~(R - 1)) : fv0;
+  const int ng = fv1 >= fv0 ? (fv1 - fb) / R + 1 : 0;
+  const int nbulk = fv1 >= fv0 ? ng * nl : 0, nedge = (e.lo || e.hi) ? 2 * nl : 0;
   const float inv = 1.0f / (float)(XDIR ? ng : nl);
   b.par(nbulk + nedge, [&](int t) {
     if (t < nbulk) {
@@ -93,27 +115,20 @@ FV_DEV void ppm_sweep(const Block &b, const double *Qs, int sj, const double *cg
       const int l = l0 + (XDIR ? hi_ : lo_), gi = XDIR ? lo_ : hi_;
       const int F0 = fb + gi * R;
       const int p0 = F0 * st + l * ls;
-      // window w[n] = q[F0 - 4 + n], n = 0..9 (w[0] only completes the aligned pair of an x sweep)
+      // window w[n] = q[F0 - 4 + n], n = 0..9 (w[0] only completes the aligned pair of an x sweep).  Loads are
+      // unconditional: a window may reach into the guard doubles around the planes (plane.h) or a neighbouring row,
+      // the faces computed from such values lie outside [fv0, fv1] and are dropped.
       double w[R + 6];
+      double c[R];
       if (XDIR) {
 #pragma unroll
-        for (int n = 0; n < R + 6; n += 2) {
-          w[n] = w[n + 1] = 0.0;
-          if (F0 - 4 + n >= v0 && F0 - 4 + n + 1 < v1) ld_pair(Qs + p0 - 4 + n, w[n], w[n + 1]);
-        }
+        for (int n = 0; n < R + 6; n += 2) ld_pair(Qs + p0 - 4 + n, w[n], w[n + 1]);
       } else {
 #pragma unroll
-        for (int n = 1; n < R + 6; ++n) {
-          w[n] = 0.0;
-          if (F0 - 4 + n >= v0 && F0 - 4 + n < v1) w[n] = Qs[p0 + (n - 4) * st];
-        }
+        for (int n = 1; n < R + 6; ++n) w[n] = Qs[p0 + (n - 4) * st];
       }
-      double c[R];
 #pragma unroll
-      for (int n = 0; n < R; ++n) {
-        const int f = F0 + n;
-        c[n] = (f >= f0 && f <= f1) ? FV_LDG(cg + p0 + n * st) : 0.0;
-      }
+      for (int n = 0; n < R; ++n) c[n] = FV_LDG(cg + p0 + n * st);
       if (MORD < 8) {
         // al at faces F0-1 .. F0+R: al[m] is the edge value at face F0 - 1 + m; q[f] = w[f - F0 + 4]
         double al[R + 2];
@@ -121,8 +136,7 @@ FV_DEV void ppm_sweep(const Block &b, const double *Qs, int sj, const double *cg
         for (int m = 0; m < R + 2; ++m) al[m] = PPM_P1 * (w[m + 2] + w[m + 3]) + PPM_P2 * (w[m + 1] + w[m + 4]);
 #pragma unroll
         for (int n = 0; n < R; ++n) {
-          const int f = F0 + n;
-          if (f < f0 || f > f1 || (f >= elo0 && f <= elo1) || (f >= ehi0 && f <= ehi1)) continue;
+          if ((unsigned)(F0 + n - fv0) > nfv) continue;
           fin(p0 + n * st, ppm_face_lt8<MORD>(c[n], w[n + 3], w[n + 4], al[n], al[n + 1], al[n + 2]));
         }
       } else {
@@ -132,8 +146,7 @@ FV_DEV void ppm_sweep(const Block &b, const double *Qs, int sj, const double *cg
         for (int m = 0; m < R + 3; ++m) dm[m] = ppm_dm8v(w[m + 1], w[m + 2], w[m + 3]);
 #pragma unroll
         for (int n = 0; n < R; ++n) {
-          const int f = F0 + n;
-          if (f < f0 || f > f1 || (f >= elo0 && f <= elo1) || (f >= ehi0 && f <= ehi1)) continue;
+          if ((unsigned)(F0 + n - fv0) > nfv) continue;
           const bool pos = c[n] > 0.0;
           // upwind cell: f - 1 (w[n + 3], dm[n + 1]) for c > 0, else f (w[n + 4], dm[n + 2])
           const double qm = pos ? w[n + 2] : w[n + 3], q0 = pos ? w[n + 3] : w[n + 4], qq = pos ? w[n + 4] : w[n + 5];
@@ -142,22 +155,46 @@ FV_DEV void ppm_sweep(const Block &b, const double *Qs, int sj, const double *cg
         }
       }
     } else {
-      // faces next to a cube-tile edge: one-sided edge values / bl, br (xppm.py:148-181, 185-246)
+      // faces next to a cube-tile edge: one-sided edge values / bl, br (xppm.py:148-181, 185-246).  One task per
+      // (line, tile edge) = 3 faces.
       const int t2 = t - nbulk;
-      const int l = l0 + t2 / 6, r = t2 % 6;
-      if (r < 3 ? !e.lo : !e.hi) return;
-      const int f = r < 3 ? e.start + r : e.end - 1 + (r - 3);
-      if (r >= 3 && e.lo && f <= e.start + 2) return;  // tiny domains: already done by the low-edge tasks
-      if (f < f0 || f > f1) return;
-      const int p = f * st + l * ls;
-      auto q = [&](int ii) { return Qs[ii * st + l * ls]; };
-      auto dx = [&](int ii) { return dxg[ii * st + l * ls]; };
-      if (MORD < 8) {
-        auto al = [&](int ii) { return ppm_al_lt8(q, dx, ii, e); };
-        fin(p, ppm_flux_staged<MORD>(q, al, dx, cg[p], f, e));
-      } else {
-        auto dm = [&](int ii) { return ppm_dm8(q, ii); };
-        fin(p, ppm_flux_staged<8>(q, dm, dx, cg[p], f, e));
+      const int l = l0 + (t2 >> 1);
+      const bool high = t2 & 1;
+      if (high ? !e.hi : !e.lo) return;
+      const int fa = high ? e.end - 1 : e.start;  // faces fa .. fa + 2
+      if (MORD < 8 && fa >= f0 && fa + 2 <= f1 && e.end - e.start >= 6) {
+        // straight-line form of compute_al (xppm.py:148-181) around the edge: a = first of the three special faces
+        const int a = high ? e.end : e.start - 1;
+        const int pa = a * st + l * ls;
+        const double *qa = Qs + pa, *da = dxg + pa;
+        const double qm4 = high ? qa[-4 * st] : 0.0, qm3 = high ? qa[-3 * st] : 0.0;
+        const double qm2 = qa[-2 * st], qm1 = qa[-st], q0 = qa[0], q1 = qa[st], q2 = qa[2 * st], q3 = qa[3 * st];
+        const double q4 = high ? 0.0 : qa[4 * st], q5 = high ? 0.0 : qa[5 * st];
+        const double dm1 = FV_LDG(da - st), d0 = FV_LDG(da), d1 = FV_LDG(da + st), d2 = FV_LDG(da + 2 * st);
+        const double al_a = PPM_C1 * qm2 + PPM_C2 * qm1 + PPM_C3 * q0;
+        const double al_a1 = 0.5 * (((2.0 * d0 + dm1) * q0 - d0 * qm1) / (dm1 + d0) + ((2.0 * d1 + d2) * q1 - d1 * q2) / (d1 + d2));
+        const double al_a2 = PPM_C3 * q1 + PPM_C2 * q2 + PPM_C1 * q3;
+        if (!high) {
+          const double al_a3 = PPM_P1 * (q2 + q3) + PPM_P2 * (q1 + q4), al_a4 = PPM_P1 * (q3 + q4) + PPM_P2 * (q2 + q5);
+          // faces a+1, a+2, a+3
+          fin(pa + st, ppm_face_lt8<MORD>(cg[pa + st], q0, q1, al_a, al_a1, al_a2));
+          fin(pa + 2 * st, ppm_face_lt8<MORD>(cg[pa + 2 * st], q1, q2, al_a1, al_a2, al_a3));
+          fin(pa + 3 * st, ppm_face_lt8<MORD>(cg[pa + 3 * st], q2, q3, al_a2, al_a3, al_a4));
+        } else {
+          const double al_m2 = PPM_P1 * (qm3 + qm2) + PPM_P2 * (qm4 + qm1), al_m1 = PPM_P1 * (qm2 + qm1) + PPM_P2 * (qm3 + q0);
+          // faces a-1, a, a+1
+          fin(pa - st, ppm_face_lt8<MORD>(cg[pa - st], qm2, qm1, al_m2, al_m1, al_a));
+          fin(pa, ppm_face_lt8<MORD>(cg[pa], qm1, q0, al_m1, al_a, al_a1));
+          fin(pa + st, ppm_face_lt8<MORD>(cg[pa + st], q0, q1, al_a, al_a1, al_a2));
+        }
+        return;
+      }
+      for (int r = 0; r < 3; ++r) {
+        const int f = fa + r;
+        if (high && e.lo && f <= e.start + 2) continue;  // tiny domains: already done by the low-edge task
+        if (f < f0 || f > f1) continue;
+        const int p = f * st + l * ls;
+        fin(p, ppm_edge_face<MORD>(Qs + l * ls, dxg + l * ls, st, cg[p], f, e));
       }
     }
   });
