@@ -3,13 +3,15 @@
 //   fv3_divergence_damping <- DivergenceDamping.__call__ (divergence_damping.py:482-632)
 //   fv3_a2b_ord4           <- AGrid2BGridFourthOrder.__call__ (a2b_ord4.py:673-761)
 // Sub-stages call the same internal routines as the stand-alone entry points (fxadv.cu, fvtp2d.cu).
-#include "a2b.h"
-#include "common.h"
-#include "plane.h"
-#include "ppm.h"
+#include <type_traits>
 
-extern "C" int fv3_fv_prep(fv3_ctx *, const double *, const double *, double *, double *, double *, double *, double *,
-                           double *, double, void *);
+#include "a2b.h"
+#include "transport.h"
+
+namespace fv3 {
+int fv_prep_launch(fv3_ctx *ctx, cudaStream_t st, const double *uc, const double *vc, double *crx, double *cry, double *xfx,
+                   double *yfx, double *ucc_out, double *vcc_out, double *cx, double *cy, double dt, bool store_all);
+}
 extern "C" int fv3_fvtp2d(fv3_ctx *, const double *, const double *, const double *, const double *, const double *,
                           double *, double *, const double *, const double *, const double *, int, const double *,
                           const double *, int, int, void *);
@@ -267,6 +269,157 @@ FV_HD double advect_along(int mord, Q q, DXE dxe, Z zero, double ub, double cfl,
   return ub > 0.0 ? ql + fx0 * mask : qr + fx0 * mask;
 }
 
+
+struct Fields4 {
+  double *f[4];
+};
+
+// Rows of an in-place update that another strip of the same plane still reads as halo are written to a side buffer
+// (plane-for-plane copy of the field) and copied back by this launch once every strip is done.
+void unpark_rows(const fv3_ctx *ctx, cudaStream_t st, Fields4 fl, int nf, double *side0, int nk) {
+  const fv3_geom g = ctx->g;
+  const fv3::StripGeom sg = fv3::strip_geometry(g, fv3::FVTP_PLANES);
+  if (sg.ns <= 1) return;
+  const int64_t side_stride = g.ss * g.n_sub;
+  const int h = g.halo, R = sg.rows_per_strip;
+  fv3::launch3d(ctx, st, h, h + g.nx, 0, 2 * h * (sg.ns - 1), 0, nk, FV_LAMBDA(int s, int i, int jj, int k) { FV_DEV_GM
+    const int h2 = g.halo, bnd = jj / (2 * h2), j = h2 + (bnd + 1) * R - h2 + (jj - bnd * 2 * h2);
+    if (j >= h2 + g.ny) return;
+    const int64_t o = O3(s, i, j, k);
+    for (int n = 0; n < nf; ++n) fl.f[n][o] = side0[n * side_stride + o];
+  });
+}
+
+// ---- K2: the four flux-form transports of d_sw (delp, w, q_con, pt) and everything between them, ONE strip-resident
+// kernel (d_sw.py:967-1090): delp transport + del-n damping -> mass fluxes (kept in a scratch field that stays in L2,
+// accumulated into mfx / mfy: flux_capacitor :29-50); del-n fluxes of damp_w * w and the heat they dissipate (:53-103);
+// w, q_con, pt transports with the mass fluxes, their del-n damping, and the flux-form updates of all four fields
+// (apply_fluxes, apply_pt_delp_fluxes, adjust_w_and_qcon :106-160,331-346).  Compulsory traffic: 4 fields read and
+// written, 4 Courant / area-flux fields read, mfx / mfy read-modify-write, heat written.
+// The eight steps run as ONE loop around a single transport body and a single del-n body (a step table selects the
+// field and the operands), so that the kernel holds one copy of each sweep instead of four.
+// MDP / MVT / MTM: |hord_dp|, |hord_vt|, |hord_tm| (5, 6 or 8).
+template <int MDP, int MVT, int MTM>
+int dsw_scalars_launch(fv3_ctx *ctx, cudaStream_t st, double *delp, double *pt, double *w, double *q_con, const double *crx,
+                       const double *cry, const double *xfx, const double *yfx, double *mfx, double *mfy, double *heat_s,
+                       double *diss_est, double *fxs, double *fys, double *side0, double dt, const fv3_dsw_cols *c,
+                       int rdp, int rvt, int rtm) {
+  const fv3_geom g = ctx->g;
+  const fv3_grid m = ctx->m;
+  const fv3_dsw_cols cl = *c;
+  const int64_t side_stride = g.ss * g.n_sub;
+  return fv3::launch_planes(ctx, st, 0, g.nz, fv3::FVTP_PLANES, FV_LAMBDA(int s, int k, const fv3::Block &b) { FV_DEV_GM
+    double *Q = b.plane(0), *A = b.plane(1), *B = b.plane(2), *D = b.plane(3), *T = b.plane(4);
+    const int sj = g.sj, h = g.halo, nx = g.nx;
+    const int isc = h, iec = h + nx - 1;
+    const int ja = b.ja, jb = b.jb, jt = b.jtop();
+    const int64_t ob = O3(s, 0, 0, k), o2b = O2(s, 0, 0);
+    const double *rarea = m.rarea + o2b;
+    const double *dp = delp + ob;
+    double *fxp = fxs + ob, *fyp = fys + ob;
+    const double damp_w = cl.damp_w[k];
+    // rows another strip of this plane reads as halo are parked (see unpark_rows)
+    auto parked = [&](int j) { return (j < ja + h && !b.first) || (j >= jb - h && !b.last); };
+    // new mass of a cell (apply_pt_delp_fluxes)
+    auto dp_new = [&](int p, double dp0) { return dp0 + (fxp[p] - fxp[p + 1] + fyp[p] - fyp[p + sj]) * rarea[p]; };
+    // Straight-line sequence (field pointers and column parameters stay kernel-parameter constants instead of
+    // loop-carried registers): delp | w | q_con | pt.
+    auto transport = [&](auto mord_tag, const double *q, const double *xu, const double *yu) {
+      constexpr int MO = decltype(mord_tag)::value;
+      const fv3::PlaneArgs pa{q, crx, cry, xfx, yfx, xu, yu};
+      if (MO != 0) {
+        fv3::fvtp2d_plane<MO == 0 ? 6 : MO, false>(g, m, s, k, b, pa, Q, A, B, D, T);
+      } else {
+        // mixed orders: the true |hord| of this field is a run-time value
+        const int mord = q == w ? rvt : (q == pt ? rtm : rdp);
+        if (mord == 8)
+          fv3::fvtp2d_plane<8, false>(g, m, s, k, b, pa, Q, A, B, D, T);
+        else if (mord == 5)
+          fv3::fvtp2d_plane<5, false>(g, m, s, k, b, pa, Q, A, B, D, T);
+        else
+          fv3::fvtp2d_plane<6, false>(g, m, s, k, b, pa, Q, A, B, D, T);
+      }
+    };
+    constexpr bool same = MDP == MVT && MDP == MTM;
+    typedef std::integral_constant<int, same ? MDP : 0> TagDP;
+    typedef std::integral_constant<int, same ? MVT : 0> TagVT;
+    typedef std::integral_constant<int, same ? MTM : 0> TagTM;
+    // (1) mass: delp transport + del-n damping (d_sw.py:967-975); mass fluxes kept for the other transports and
+    //     accumulated (flux_capacitor)
+    transport(TagDP(), delp, xfx, yfx);
+    fv3::delnflux_plane(g, m, s, b, dp, cl.dn_damp_vt[k], cl.nord_v[k] > 0, cl.nmax_v, false, Q, D, T);
+    b.rect(isc, iec + 2, ja, jb + 1, [&](int i, int j) {
+      const int p = j * sj + i;
+      if (j < jb) {
+        const double fl = B[p] + D[p];
+        fxp[p] = fl;
+        mfx[ob + p] = mfx[ob + p] + fl;
+      }
+      if (i <= iec) {
+        const double fl = A[p] + T[p];
+        fyp[p] = fl;  // face row jb is also the next strip's first face: both store the same value
+        if (j <= jt) mfy[ob + p] = mfy[ob + p] + fl;
+      }
+    });
+    // (2) w: del-n fluxes of damp_w * w and the heat they dissipate (d_sw.py:53-103); dw goes to T for the update
+    fv3::delnflux_plane(g, m, s, b, w + ob, cl.dn_damp_w_c[k], cl.nord_w[k] > 0, cl.nmax_w, false, Q, A, B);
+    {
+      const double dd8 = cl.ke_bg[k] * fabs(dt);
+      b.rect(isc, iec + 1, ja, jb, [&](int i, int j) {
+        const int p = j * sj + i;
+        double hs = 0.0;
+        if (damp_w > 1e-5) {
+          const double d = (A[p] - A[p + 1] + B[p] - B[p + sj]) * rarea[p];
+          T[p] = d;
+          hs = dd8 - d * (w[ob + p] + 0.5 * d);
+        }
+        heat_s[ob + p] = hs;
+        diss_est[ob + p] = hs;
+      });
+    }
+    // (3) w transport and update (apply_fluxes + adjust_w_and_qcon)
+    transport(TagVT(), w, fxs, fys);
+    b.rect(isc, iec + 1, ja, jb, [&](int i, int j) {
+      const int p = j * sj + i;
+      const int64_t o = ob + p;
+      const double dp0 = dp[p], ra = rarea[p];
+      double wv = w[o] * dp0 + (B[p] - B[p + 1] + A[p] - A[p + sj]) * ra;
+      wv = wv / dp_new(p, dp0);
+      if (damp_w > 1e-5) wv = wv + T[p];
+      (parked(j) ? side0 : w)[o] = wv;
+    });
+    // (4) q_con and (5) pt: transport, mass-weighted del-n damping (delnflux.py:1164-1207, 215-238), update
+    auto damped_update = [&](double *q, double dk, bool hi, int nmax, double *side) {
+      fv3::delnflux_plane(g, m, s, b, q + ob, dk, hi, nmax, true, Q, D, T);
+      b.rect(isc, iec + 2, ja, jb + 1, [&](int i, int j) {
+        const int p = j * sj + i;
+        if (j < jb) B[p] = B[p] + 0.5 * dk * (dp[p - 1] + dp[p]) * D[p];
+        if (i <= iec) A[p] = A[p] + 0.5 * dk * (dp[p - sj] + dp[p]) * T[p];
+      });
+      b.rect(isc, iec + 1, ja, jb, [&](int i, int j) {
+        const int p = j * sj + i;
+        const int64_t o = ob + p;
+        const double dp0 = dp[p];
+        double qv = q[o] * dp0 + (B[p] - B[p + 1] + A[p] - A[p + sj]) * rarea[p];
+        qv = qv / dp_new(p, dp0);
+        (parked(j) ? side : q)[o] = qv;
+      });
+    };
+    transport(TagDP(), q_con, fxs, fys);
+    damped_update(q_con, cl.dn_damp_t[k], cl.nord_t[k] > 0, cl.nmax_t, side0 + side_stride);
+    transport(TagTM(), pt, fxs, fys);
+    damped_update(pt, cl.dn_damp_vt[k], cl.nord_v[k] > 0, cl.nmax_v, side0 + 2 * side_stride);
+    // the new mass itself
+    {
+      double *side = side0 + 3 * side_stride;
+      b.rect(isc, iec + 1, ja, jb, [&](int i, int j) {
+        const int p = j * sj + i;
+        (parked(j) ? side : delp)[ob + p] = dp_new(p, dp[p]);
+      });
+    }
+  });
+}
+
 }  // namespace
 
 extern "C" {
@@ -312,54 +465,27 @@ int fv3_d_sw(fv3_ctx *ctx, double *delpc, double *delp, double *pt, double *u, d
   double *ut = fv3::scratch_field(ctx, 34), *vt = fv3::scratch_field(ctx, 35);
   const double *damp_w = c->damp_w, *ke_bg = c->ke_bg, *d_con = c->d_con, *damp_vt = c->damp_vt;
 
-  if ((rc = fv3_fv_prep(ctx, uc, vc, crx, cry, xfx, yfx, ucc, vcc, dt, stream))) return rc;
-  // delp transport fluxes (mass fluxes) with del-n damping (d_sw.py:967-975)
-  if ((rc = fv3_fvtp2d(ctx, delp, crx, cry, xfx, yfx, fx, fy, nullptr, nullptr, nullptr, cfg.hord_dp, c->nord_v,
-                       c->dn_damp_vt, c->nmax_v, nz, stream)))
-    return rc;
-  // flux_capacitor (d_sw.py:29-50) on the full domain
-  fv3::launch3d(ctx, st, 0, ied + 1, 0, jed + 1, 0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
-    const int64_t o = O3(s, i, j, k);
-    cx[o] = cx[o] + crx[o];
-    cy[o] = cy[o] + cry[o];
-    mfx[o] = mfx[o] + fx[o];
-    mfy[o] = mfy[o] + fy[o];
-  });
-  // w: del-n fluxes of damp_w * w, heat dissipation (d_sw.py:53-103)
-  if ((rc = fv3_delnflux_nosg(ctx, w, fx2, fy2, c->dn_damp_w_c, c->nord_w, c->nmax_w, nz, stream))) return rc;
-  fv3::launch3d(ctx, st, isc, iec + 1, jsc, jec + 1, 0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
-    const int64_t o = O3(s, i, j, k);
-    double hs = 0.0;
-    if (damp_w[k] > 1e-5) {
-      const double dd8 = ke_bg[k] * fabs(dt);
-      const double d = (fx2[o] - fx2[o + 1] + fy2[o] - fy2[o + sj]) * m.rarea[O2(s, i, j)];
-      dw[o] = d;
-      hs = dd8 - d * (w[o] + 0.5 * d);
-    }
-    heat_s[o] = hs;
-    diss_est[o] = hs;
-  });
-  if ((rc = fv3_fvtp2d(ctx, w, crx, cry, xfx, yfx, gxw, gyw, fx, fy, nullptr, cfg.hord_vt, nullptr, nullptr, 0, nz, stream))) return rc;
-  if ((rc = fv3_fvtp2d(ctx, q_con, crx, cry, xfx, yfx, gxq, gyq, fx, fy, delp, cfg.hord_dp, c->nord_t, c->dn_damp_t, c->nmax_t, nz, stream))) return rc;
-  if ((rc = fv3_fvtp2d(ctx, pt, crx, cry, xfx, yfx, gxp, gyp, fx, fy, delp, cfg.hord_tm, c->nord_v, c->dn_damp_vt, c->nmax_v, nz, stream))) return rc;
-  // apply_fluxes (w, q_con), apply_pt_delp_fluxes, adjust_w_and_qcon (d_sw.py:106-160,331-346) on the compute domain
-  fv3::launch3d(ctx, st, isc, iec + 1, jsc, jec + 1, 0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
-    const int64_t o = O3(s, i, j, k);
-    const double ra = m.rarea[O2(s, i, j)];
-    const double dp0 = delp[o];
-    double wv = w[o] * dp0 + (gxw[o] - gxw[o + 1] + gyw[o] - gyw[o + sj]) * ra;
-    double qc = q_con[o] * dp0 + (gxq[o] - gxq[o + 1] + gyq[o] - gyq[o + sj]) * ra;
-    double ptv = pt[o] * dp0 + (gxp[o] - gxp[o + 1] + gyp[o] - gyp[o + sj]) * ra;
-    const double dp1 = dp0 + (fx[o] - fx[o + 1] + fy[o] - fy[o + sj]) * ra;
-    ptv = ptv / dp1;
-    wv = wv / dp1;
-    if (damp_w[k] > 1e-5) wv = wv + dw[o];
-    qc = qc / dp1;
-    delp[o] = dp1;
-    pt[o] = ptv;
-    w[o] = wv;
-    q_con[o] = qc;
-  });
+  // K1: contravariant winds, Courant numbers, area fluxes; cx += crx, cy += cry (fxadv.py:565-661, d_sw.py:29-50)
+  if ((rc = fv3::fv_prep_launch(ctx, st, uc, vc, crx, cry, xfx, yfx, ucc, vcc, cx, cy, dt, false))) return rc;
+  // K2: delp, w, q_con, pt transports and updates (d_sw.py:967-1090)
+  double *side0 = fv3::scratch_field(ctx, 0);
+  {
+    auto mo = [](int hord) { const int a = hord < 0 ? -hord : hord; return a == 10 ? 8 : a; };
+    const int mdp = mo(cfg.hord_dp), mvt = mo(cfg.hord_vt), mtm = mo(cfg.hord_tm);
+#define DSW_SCALARS(A_, B_, C_) \
+  dsw_scalars_launch<A_, B_, C_>(ctx, st, delp, pt, w, q_con, crx, cry, xfx, yfx, mfx, mfy, heat_s, diss_est, fx, fy, side0, dt, c, mdp, mvt, mtm)
+    if (mdp == 6 && mvt == 6 && mtm == 6)
+      rc = DSW_SCALARS(6, 6, 6);
+    else if (mdp == 5 && mvt == 5 && mtm == 5)
+      rc = DSW_SCALARS(5, 5, 5);
+    else if (mdp == 8 && mvt == 8 && mtm == 8)
+      rc = DSW_SCALARS(8, 8, 8);
+    else
+      rc = DSW_SCALARS(0, 1, 2);  // mixed orders: one kernel with all three sweep bodies, selected per field
+#undef DSW_SCALARS
+    if (rc) return rc;
+  }
+  unpark_rows(ctx, st, Fields4{{w, q_con, pt, delp}}, 4, side0, nz);
   // kinetic energy on cell corners (d_sw.py:204-298)
   const int mord = cfg.hord_mt < 0 ? -cfg.hord_mt : cfg.hord_mt;
   if (mord >= 8) {
