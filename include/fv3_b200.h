@@ -110,6 +110,15 @@ int fv3_halo_pack(const fv3_geom *geom, double *const *fields, int n_fields, int
                   const int8_t *src_comp, const double *sign, int64_t n_entries, double *buf, void *stream);
 int fv3_halo_unpack(const fv3_geom *geom, double *const *fields, int n_fields, int nlev, const int64_t *dst_off,
                     const int8_t *dst_comp, int64_t n_entries, const double *buf, void *stream);
+/* segmented forms: ONE launch per exchange for all peer GPUs.  buf holds one contiguous segment per peer (the NCCL
+ * send / recv message, halo_updater.py:217-303 posts one Isend/Irecv per neighbour); entry e lives at
+ *   buf[seg_base[e] + (f*nlev + k)*seg_n[e] + seg_e[e]].                                                   */
+int fv3_halo_pack_segments(const fv3_geom *geom, double *const *fields, int n_fields, int nlev, const int64_t *src_off,
+                           const int8_t *src_comp, const double *sign, const int64_t *seg_base, const int32_t *seg_n,
+                           const int32_t *seg_e, int64_t n_entries, double *buf, void *stream);
+int fv3_halo_unpack_segments(const fv3_geom *geom, double *const *fields, int n_fields, int nlev, const int64_t *dst_off,
+                             const int8_t *dst_comp, const int64_t *seg_base, const int32_t *seg_n, const int32_t *seg_e,
+                             int64_t n_entries, const double *buf, void *stream);
 
 /* ---- NonhydrostaticVerticalSolverCGrid.__call__ (fv3core/pace/fv3core/stencils/riem_solver_c.py:172-250) */
 int fv3_riem_solver_c(fv3_ctx *ctx, double dt2, const double *cappa, double ptop, const double *hs,

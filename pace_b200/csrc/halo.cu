@@ -53,4 +53,49 @@ int fv3_halo_unpack(const fv3_geom *geom, double *const *fields, int n_fields, i
   return fv3::check_launch("fv3_halo_unpack");
 }
 
+// Segmented forms: ONE launch per exchange covers every peer process.  The buffer holds one contiguous segment per peer
+// (what NCCL sends / receives); entry e belongs to the segment starting at seg_base[e] (doubles) that holds seg_n[e]
+// entries per (field, level), and is the seg_e[e]-th of them:
+//   buf[seg_base[e] + (f * nlev + k) * seg_n[e] + seg_e[e]]
+int fv3_halo_pack_segments(const fv3_geom *geom, double *const *fields, int n_fields, int nlev, const int64_t *src_off,
+                           const int8_t *src_comp, const double *sign, const int64_t *seg_base, const int32_t *seg_n,
+                           const int32_t *seg_e, int64_t n_entries, double *buf, void *stream) {
+  const int64_t sk = nlev > 1 ? geom->sk : 0;
+  fv3::launch1d((cudaStream_t)stream, n_entries, (nlev + HALO_KB - 1) / HALO_KB, n_fields, FV_LAMBDA(int64_t e, int kb, int f) {
+    const double *src = fields[src_comp[e] * n_fields + f] + src_off[e];
+    const double sg = sign[e];
+    const int64_t n = seg_n[e];
+    double *dst = buf + seg_base[e] + (int64_t)f * nlev * n + seg_e[e];
+    const int k0 = kb * HALO_KB;
+    double v[HALO_KB];
+#pragma unroll
+    for (int q = 0; q < HALO_KB; ++q)
+      if (k0 + q < nlev) v[q] = src[(k0 + q) * sk];
+#pragma unroll
+    for (int q = 0; q < HALO_KB; ++q)
+      if (k0 + q < nlev) dst[(k0 + q) * n] = sg * v[q];
+  });
+  return fv3::check_launch("fv3_halo_pack_segments");
+}
+
+int fv3_halo_unpack_segments(const fv3_geom *geom, double *const *fields, int n_fields, int nlev, const int64_t *dst_off,
+                             const int8_t *dst_comp, const int64_t *seg_base, const int32_t *seg_n, const int32_t *seg_e,
+                             int64_t n_entries, const double *buf, void *stream) {
+  const int64_t sk = nlev > 1 ? geom->sk : 0;
+  fv3::launch1d((cudaStream_t)stream, n_entries, (nlev + HALO_KB - 1) / HALO_KB, n_fields, FV_LAMBDA(int64_t e, int kb, int f) {
+    double *dst = fields[dst_comp[e] * n_fields + f] + dst_off[e];
+    const int64_t n = seg_n[e];
+    const double *src = buf + seg_base[e] + (int64_t)f * nlev * n + seg_e[e];
+    const int k0 = kb * HALO_KB;
+    double v[HALO_KB];
+#pragma unroll
+    for (int q = 0; q < HALO_KB; ++q)
+      if (k0 + q < nlev) v[q] = src[(k0 + q) * n];
+#pragma unroll
+    for (int q = 0; q < HALO_KB; ++q)
+      if (k0 + q < nlev) dst[(k0 + q) * sk] = v[q];
+  });
+  return fv3::check_launch("fv3_halo_unpack_segments");
+}
+
 }  // extern "C"

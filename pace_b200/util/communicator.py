@@ -7,9 +7,11 @@ Keeps the reference API for the halo path (util/pace/util/communicator.py:331-55
 Design: the gather table of pace_b200.util.topology is split by where source and destination live:
   same process  -> ONE `fv3_halo_gather` launch that reads the neighbour subdomain's array directly (rotation,
                    component swap and sign folded into the table; no staging buffer);
-  other process -> ONE `fv3_halo_pack` launch per exchange into a buffer holding one contiguous segment per
-                   peer, NCCL send/recv of the segments (torch.distributed batch_isend_irecv), ONE
-                   `fv3_halo_unpack` launch on wait().
+  other process -> ONE `fv3_halo_pack_segments` launch per exchange into a buffer holding one contiguous segment per
+                   peer, NCCL send/recv of the segments (torch.distributed batch_isend_irecv, one grouped call),
+                   ONE `fv3_halo_unpack_segments` launch on wait().  Pack, NCCL and unpack run on a dedicated
+                   communication stream ordered against the compute stream by events, so everything the caller
+                   enqueues between start() and wait() overlaps the inter-GPU exchange.
 """
 import ctypes
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -116,22 +118,39 @@ class HaloUpdater:
             src_comp=dev_t(table.src_comp[m], torch.int8),
             sign=dev_t(table.sign[m], torch.float64),
         )
-        # remote parts: canonical order = table order restricted to the (src_proc, dst_proc) pair
-        self._send = []  # (peer, n, src_off, src_comp, sign)
-        self._recv = []  # (peer, n, dst_off, dst_comp)
-        for peer in range(pc.size):
-            if peer == me:
-                continue
-            ms = (src_proc == me) & (dst_proc == peer)
-            if ms.any():
-                self._send.append((peer, int(ms.sum()),
-                                   dev_t(off(table.src_rank[ms], table.src_i[ms], table.src_j[ms]), torch.int64),
-                                   dev_t(table.src_comp[ms], torch.int8), dev_t(table.sign[ms], torch.float64)))
-            mr = (dst_proc == me) & (src_proc == peer)
-            if mr.any():
-                self._recv.append((peer, int(mr.sum()),
-                                   dev_t(off(table.dst_rank[mr], table.dst_i[mr], table.dst_j[mr]), torch.int64),
-                                   dev_t(table.dst_comp[mr], torch.int8)))
+        # remote parts: canonical order = table order restricted to the (src_proc, dst_proc) pair; all peers of one
+        # direction share ONE table (one launch), each peer owning a contiguous segment of the message buffer
+        def segments(mine, other, rank_a, i_a, j_a, comp_a, with_sign):
+            peers, offs, comps, signs, seg_n, seg_e, seg_peer = [], [], [], [], [], [], []
+            for peer in range(pc.size):
+                if peer == me:
+                    continue
+                msk = (mine == me) & (other == peer)
+                n = int(msk.sum())
+                if n == 0:
+                    continue
+                peers.append((peer, n))
+                offs.append(off(rank_a[msk], i_a[msk], j_a[msk]))
+                comps.append(comp_a[msk])
+                signs.append(table.sign[msk])
+                seg_n.append(np.full(n, n, dtype=np.int32))
+                seg_e.append(np.arange(n, dtype=np.int32))
+                seg_peer.append(np.full(n, len(peers) - 1, dtype=np.int64))
+            if not peers:
+                return None
+            return dict(peers=peers, off=np.concatenate(offs), comp=np.concatenate(comps), sign=np.concatenate(signs),
+                        seg_n=np.concatenate(seg_n), seg_e=np.concatenate(seg_e), seg_peer=np.concatenate(seg_peer))
+
+        self._send = segments(src_proc, dst_proc, table.src_rank, table.src_i, table.src_j, table.src_comp, True)
+        self._recv = segments(dst_proc, src_proc, table.dst_rank, table.dst_i, table.dst_j, table.dst_comp, False)
+        for seg in (self._send, self._recv):
+            if seg is not None:
+                seg["d_off"] = dev_t(seg["off"], torch.int64)
+                seg["d_comp"] = dev_t(seg["comp"], torch.int8)
+                seg["d_sign"] = dev_t(seg["sign"], torch.float64)
+                seg["d_seg_n"] = dev_t(seg["seg_n"], torch.int32)
+                seg["d_seg_e"] = dev_t(seg["seg_e"], torch.int32)
+                seg["n"] = int(len(seg["off"]))
         self._bufs: Dict[int, tuple] = {}
         self._ptr_cache: Dict[tuple, torch.Tensor] = {}
         self._pending = None
@@ -147,12 +166,23 @@ class HaloUpdater:
         return t
 
     def _buffers(self, n_fields):
+        """Message buffers of one exchange with n_fields fields: (send buffer, per-peer send views, segment bases on the
+        device) and the same for the receive side."""
         b = self._bufs.get(n_fields)
         if b is None:
             dev = self._comm.device
-            sb = [torch.empty(n_fields * self._nlev * n, dtype=torch.float64, device=dev) for (_, n, *_r) in self._send]
-            rb = [torch.empty(n_fields * self._nlev * n, dtype=torch.float64, device=dev) for (_, n, *_r) in self._recv]
-            b = (sb, rb)
+
+            def make(seg):
+                if seg is None:
+                    return None
+                per = n_fields * self._nlev
+                starts = np.cumsum([0] + [n * per for _, n in seg["peers"]])
+                buf = torch.empty(int(starts[-1]), dtype=torch.float64, device=dev)
+                views = [buf[int(starts[p]):int(starts[p + 1])] for p in range(len(seg["peers"]))]
+                base = torch.as_tensor(starts[:-1][seg["seg_peer"]].astype(np.int64)).to(dev)
+                return buf, views, base
+
+            b = (make(self._send), make(self._recv))
             self._bufs[n_fields] = b
         return b
 
@@ -167,28 +197,36 @@ class HaloUpdater:
         if self._vector and len(quantities_y) != n_fields:
             raise ValueError("quantities_x and quantities_y must have the same length")
         ptrs = self._field_ptrs(quantities_x, quantities_y)
-        stream = comm.stream_ptr()
         gp = ctypes.byref(comm.c_geom)
         self._inflight = True
         reqs = []
         prof = _lib.PROFILE
         e0 = prof.begin() if prof is not None else None
-        if self._send or self._recv:
+        remote = self._send is not None or self._recv is not None
+        if remote:
             import torch.distributed as dist
 
             sb, rb = self._buffers(n_fields)
-            for (peer, n, src_off, src_comp, sign), buf in zip(self._send, sb):
-                _lib.check(lib, lib.fv3_halo_pack(gp, ptrs.data_ptr(), n_fields, self._nlev, src_off.data_ptr(),
-                                                  src_comp.data_ptr(), sign.data_ptr(), n, buf.data_ptr(), stream),
-                           "fv3_halo_pack")
-            ops = [dist.P2POp(dist.isend, buf, peer, comm.process_comm.group) for (peer, *_), buf in zip(self._send, sb)]
-            ops += [dist.P2POp(dist.irecv, buf, peer, comm.process_comm.group) for (peer, *_), buf in zip(self._recv, rb)]
-            reqs = dist.batch_isend_irecv(ops)
+            with comm.comm_stream_context() as cstream:   # fork: the exchange runs beside the compute stream
+                ops = []
+                if self._send is not None:
+                    S = self._send
+                    buf, views, base = sb
+                    _lib.check(lib, lib.fv3_halo_pack_segments(
+                        gp, ptrs.data_ptr(), n_fields, self._nlev, S["d_off"].data_ptr(), S["d_comp"].data_ptr(),
+                        S["d_sign"].data_ptr(), base.data_ptr(), S["d_seg_n"].data_ptr(), S["d_seg_e"].data_ptr(), S["n"],
+                        buf.data_ptr(), cstream), "fv3_halo_pack_segments")
+                    ops += [dist.P2POp(dist.isend, v, peer, comm.process_comm.group) for (peer, _), v in zip(S["peers"], views)]
+                if self._recv is not None:
+                    ops += [dist.P2POp(dist.irecv, v, peer, comm.process_comm.group)
+                            for (peer, _), v in zip(self._recv["peers"], rb[1])]
+                reqs = dist.batch_isend_irecv(ops)
         if self._n_local:
             L = self._loc
             _lib.check(lib, lib.fv3_halo_gather(gp, ptrs.data_ptr(), n_fields, self._nlev, L["dst_off"].data_ptr(),
                                                 L["src_off"].data_ptr(), L["dst_comp"].data_ptr(),
-                                                L["src_comp"].data_ptr(), L["sign"].data_ptr(), self._n_local, stream),
+                                                L["src_comp"].data_ptr(), L["sign"].data_ptr(), self._n_local,
+                                                comm.stream_ptr()),
                        "fv3_halo_gather")
         self._pending = (reqs, ptrs, n_fields)
         if prof is not None:
@@ -198,16 +236,20 @@ class HaloUpdater:
         if not self._inflight:
             raise RuntimeError("HaloUpdater.wait called before start")
         reqs, ptrs, n_fields = self._pending
-        if reqs:
+        if self._send is not None or self._recv is not None:
             lib = _lib.load()
-            for r in reqs:
-                r.wait()
-            _, rb = self._buffers(n_fields)
-            gp = ctypes.byref(self._comm.c_geom)
-            stream = self._comm.stream_ptr()
-            for (peer, n, dst_off, dst_comp), buf in zip(self._recv, rb):
-                _lib.check(lib, lib.fv3_halo_unpack(gp, ptrs.data_ptr(), n_fields, self._nlev, dst_off.data_ptr(),
-                                                    dst_comp.data_ptr(), n, buf.data_ptr(), stream), "fv3_halo_unpack")
+            comm = self._comm
+            with comm.comm_stream_context(join=True, fork=True) as cstream:  # unpack after every earlier reader of the halos
+                for r in reqs:
+                    r.wait()
+                if self._recv is not None:
+                    R = self._recv
+                    buf, _, base = self._buffers(n_fields)[1]
+                    gp = ctypes.byref(comm.c_geom)
+                    _lib.check(lib, lib.fv3_halo_unpack_segments(
+                        gp, ptrs.data_ptr(), n_fields, self._nlev, R["d_off"].data_ptr(), R["d_comp"].data_ptr(),
+                        base.data_ptr(), R["d_seg_n"].data_ptr(), R["d_seg_e"].data_ptr(), R["n"], buf.data_ptr(), cstream),
+                        "fv3_halo_unpack_segments")
         self._pending = None
         self._inflight = False
 
@@ -220,6 +262,33 @@ class HaloUpdater:
             import warnings
 
             warnings.warn("HaloUpdater garbage-collected while an exchange was in flight")
+
+
+class _CommStream:
+    def __init__(self, comm, fork, join):
+        self.comm, self.fork, self.join = comm, fork, join
+
+    def __enter__(self):
+        comm = self.comm
+        if comm.device.type != "cuda":
+            return 0
+        if getattr(comm, "_comm_stream", None) is None:
+            comm._comm_stream = torch.cuda.Stream(comm.device)
+        self.main = torch.cuda.current_stream(comm.device)
+        if self.fork:
+            comm._comm_stream.wait_stream(self.main)
+        self.ctx = torch.cuda.stream(comm._comm_stream)
+        self.ctx.__enter__()
+        return comm._comm_stream.cuda_stream
+
+    def __exit__(self, *exc):
+        comm = self.comm
+        if comm.device.type != "cuda":
+            return False
+        self.ctx.__exit__(*exc)
+        if self.join:
+            self.main.wait_stream(comm._comm_stream)
+        return False
 
 
 def _stagger(dims):
@@ -263,6 +332,12 @@ class CubedSphereCommunicator:
         if self.device.type == "cuda":
             return torch.cuda.current_stream(self.device).cuda_stream
         return 0
+
+    def comm_stream_context(self, fork: bool = True, join: bool = False):
+        """Context manager that makes the communication stream current (CPU: a no-op yielding stream 0).
+        fork: the communication stream first waits for everything enqueued on the compute stream so far;
+        join: on exit the compute stream waits for everything enqueued on the communication stream."""
+        return _CommStream(self, fork, join)
 
     def _table(self, n_halo, sx, sy, mode):
         key = (n_halo, sx, sy, mode)

@@ -64,7 +64,8 @@ def load(case):
     return meta, grids, s0, s1
 
 
-def build(meta, grids, s0, dev=None):
+def build(meta, grids, s0, dev=None, process_comm=None):
+    """`process_comm`: several processes (GPUs) share the case; grids / s0 are then sliced to the local subdomains."""
     from pace_b200.fv3core._config import baroclinic_config
     from pace_b200.fv3core.dycore_state import DycoreState
     from pace_b200.fv3core.runtime import Runtime
@@ -73,7 +74,10 @@ def build(meta, grids, s0, dev=None):
     from pace_b200.util.grid.helper import DampingCoefficients, GridData
 
     nx, layout = meta["nx"], meta["layout"]
-    comm, qf = H.make_comm(nx, layout, 79, dev)
+    comm, qf = H.make_comm(nx, layout, 79, dev, process_comm=process_comm)
+    if process_comm is not None:
+        grids = [grids[r] for r in comm.local_ranks]
+        s0 = [s0[r] for r in comm.local_ranks]
     gd = GridData.from_arrays(qf, grids)
     damp = DampingCoefficients.from_arrays(qf, grids)
     cfg = baroclinic_config(nx, (layout, layout), n_split=meta.get("n_split", 1), k_split=meta.get("k_split", 1))
@@ -84,8 +88,9 @@ def build(meta, grids, s0, dev=None):
     return dycore, state
 
 
-def compare(out, s1, meta, fields=None):
-    """(failures, achieved): achieved[field] = (worst relative error over points above the floor, worst |diff|)."""
+def compare(out, s1, meta, fields=None, first_rank=0):
+    """(failures, achieved): achieved[field] = (worst relative error over points above the floor, worst |diff|).
+    `out[field][r - first_rank]` is compared with the reference rank r."""
     n = meta["nx"] // meta["layout"]
     levels = meta.get("levels")
     fields = fields or meta.get("fields") or [f for f in next(iter(s1.values())) if f in out]
@@ -94,7 +99,7 @@ def compare(out, s1, meta, fields=None):
         rel, floor = TOL.get(name, TOL["default"])
         worst_rel = worst_abs = 0.0
         for r, z in s1.items():
-            a, b = out[name][r], z[name]
+            a, b = out[name][r - first_rank], z[name]
             if a.ndim == 3:
                 nk = 80 if name in ("pe", "peln", "pk") else 79
                 ii = slice(3, 3 + n + (1 if name == "v" else 0))
