@@ -82,6 +82,14 @@ typedef struct fv3_dsw_cols {
   int32_t nonzero_nord_k, nonzero_nord;  /* first level with nord > 0 and its nord (divergence_damping.py:216-223) */
 } fv3_dsw_cols;
 
+/* SatAdjustConfig (fv3core/pace/fv3core/_config.py:16-40): the externals and time scales of the fast saturation
+ * adjustment. */
+typedef struct fv3_sat_adjust_config {
+  int32_t hydrostatic, rad_snow, rad_rain, rad_graupel, tintqs, icloud_f;
+  double sat_adj0, ql_gen, qs_mlt, ql0_max, t_sub, qi_gen, qi_lim, qi0_max, dw_ocean, dw_land, cld_min;
+  double tau_i2s, tau_v2l, tau_r2g, tau_l2r, tau_l2v, tau_imlt, tau_smlt;
+} fv3_sat_adjust_config;
+
 typedef struct fv3_ctx fv3_ctx;
 
 /* scratch: device buffer of scratch_bytes used for stage-private temporaries (never freed here). */
@@ -251,6 +259,13 @@ int fv3_tracer_subcycle(fv3_ctx *ctx, double *const *tracers, int nq, double *dp
 
 /* ---- CubedToLatLon, c2l_ord = 4 (stencils/pace/stencils/c2l_ord.py:41-66); the u/v halo update is done by the caller */
 int fv3_c2l_ord4(fv3_ctx *ctx, const double *u, const double *v, double *ua, double *va, void *stream);
+
+/* ---- SatAdjust3d.__call__ (saturation_adjustment.py:945-1108), same argument order (akap is unused there and
+ *      dropped); levels [kmp, nz) of the compute domain; te is written only when fast_mp_consv != 0. */
+int fv3_sat_adjust(fv3_ctx *ctx, const fv3_sat_adjust_config *config, double *te, double *qvapor, double *qliquid,
+                   double *qice, double *qrain, double *qsnow, double *qgraupel, double *qcld, const double *hs,
+                   const double *delp, const double *delz, double *q_con, double *pt, double *pkz, double *cappa,
+                   double r_vir, double mdt, int fast_mp_consv, int last_step, int kmp, void *stream);
 
 #ifdef __cplusplus
 }

@@ -150,7 +150,7 @@ def _stage_classes():
     from pace.fv3core.stencils import (
         a2b_ord4, c_sw, d2a2c_vect, d_sw, del2cubed, delnflux, divergence_damping, dyn_core, fillz, fvtp2d,
         fxadv, map_single, mapn_tracer, neg_adj3, nh_p_grad, pk3_halo, ray_fast, remap_profile, remapping,
-        riem_solver3, riem_solver_c, tracer_2d_1l, updatedzc, updatedzd, xppm, xtp_u, yppm, ytp_v,
+        riem_solver3, riem_solver_c, saturation_adjustment, tracer_2d_1l, updatedzc, updatedzd, xppm, xtp_u, yppm, ytp_v,
     )
     from pace.stencils import c2l_ord
 
@@ -183,6 +183,7 @@ def _stage_classes():
         "RemapProfile": remap_profile.RemapProfile,
         "Fillz": fillz.FillNegativeTracerValues,
         "NegAdj3": neg_adj3.AdjustNegativeTracerMixingRatio,
+        "SatAdjust3d": saturation_adjustment.SatAdjust3d,
         "CubedToLatLon": c2l_ord.CubedToLatLon,
     }
 

@@ -8,6 +8,35 @@ from typing import Tuple
 
 
 @dataclasses.dataclass(frozen=True)
+class SatAdjustConfig:
+    """fv3core/pace/fv3core/_config.py:16-40"""
+    hydrostatic: bool
+    rad_snow: bool
+    rad_rain: bool
+    rad_graupel: bool
+    tintqs: bool
+    sat_adj0: float
+    ql_gen: float
+    qs_mlt: float
+    ql0_max: float
+    t_sub: float
+    qi_gen: float
+    qi_lim: float
+    qi0_max: float
+    dw_ocean: float
+    dw_land: float
+    icloud_f: int
+    cld_min: float
+    tau_i2s: float
+    tau_v2l: float
+    tau_r2g: float
+    tau_l2r: float
+    tau_l2v: float
+    tau_imlt: float
+    tau_smlt: float
+
+
+@dataclasses.dataclass(frozen=True)
 class RemappingConfig:
     fill: bool
     kord_tm: int
@@ -15,7 +44,11 @@ class RemappingConfig:
     kord_wz: int
     kord_mt: int
     do_sat_adj: bool
-    hydrostatic: bool
+    sat_adjust: SatAdjustConfig
+
+    @property
+    def hydrostatic(self) -> bool:
+        return self.sat_adjust.hydrostatic
 
 
 @dataclasses.dataclass(frozen=True)
@@ -138,6 +171,32 @@ class DynamicalCoreConfig:
     nf_omega: int = 1
     fv_sg_adj: int = -1
     n_sponge: int = 1
+    # fast saturation adjustment (NamelistDefaults, util/pace/util/namelist.py:22-51)
+    tau_r2g: float = 900.0
+    tau_smlt: float = 900.0
+    tau_imlt: float = 600.0
+    tau_i2s: float = 1000.0
+    tau_l2r: float = 900.0
+    tau_l2v: float = 300.0
+    tau_v2l: float = 90.0
+    tau_g2v: float = 900.0
+    sat_adj0: float = 0.90
+    ql_gen: float = 1.0e-3
+    ql_mlt: float = 2.0e-3
+    qs_mlt: float = 1.0e-6
+    ql0_max: float = 2.0e-3
+    t_sub: float = 184.0
+    qi_gen: float = 1.82e-6
+    qi_lim: float = 1.0
+    qi0_max: float = 1.0e-4
+    rad_snow: bool = True
+    rad_rain: bool = True
+    rad_graupel: bool = True
+    tintqs: bool = False
+    dw_ocean: float = 0.10
+    dw_land: float = 0.15
+    icloud_f: int = 0
+    cld_min: float = 0.05
 
     @property
     def riemann(self) -> RiemannConfig:
@@ -162,9 +221,18 @@ class DynamicalCoreConfig:
         )
 
     @property
+    def sat_adjust(self) -> SatAdjustConfig:
+        return SatAdjustConfig(
+            hydrostatic=self.hydrostatic, rad_snow=self.rad_snow, rad_rain=self.rad_rain, rad_graupel=self.rad_graupel,
+            tintqs=self.tintqs, sat_adj0=self.sat_adj0, ql_gen=self.ql_gen, qs_mlt=self.qs_mlt, ql0_max=self.ql0_max,
+            t_sub=self.t_sub, qi_gen=self.qi_gen, qi_lim=self.qi_lim, qi0_max=self.qi0_max, dw_ocean=self.dw_ocean,
+            dw_land=self.dw_land, icloud_f=self.icloud_f, cld_min=self.cld_min, tau_i2s=self.tau_i2s, tau_v2l=self.tau_v2l,
+            tau_r2g=self.tau_r2g, tau_l2r=self.tau_l2r, tau_l2v=self.tau_l2v, tau_imlt=self.tau_imlt, tau_smlt=self.tau_smlt)
+
+    @property
     def remapping(self) -> RemappingConfig:
         return RemappingConfig(fill=self.fill, kord_tm=self.kord_tm, kord_tr=self.kord_tr, kord_wz=self.kord_wz,
-                               kord_mt=self.kord_mt, do_sat_adj=self.do_sat_adj, hydrostatic=self.hydrostatic)
+                               kord_mt=self.kord_mt, do_sat_adj=self.do_sat_adj, sat_adjust=self.sat_adjust)
 
 
 # dycore_config of driver/examples/configs/baroclinic_c12.yaml:41-88 (do_sat_adj off: SURVEY.md §8d / §8f-1)
@@ -174,6 +242,9 @@ BAROCLINIC_C12 = dict(
     hord_dp=6, hord_mt=6, hord_tm=6, hord_tr=8, hord_vt=6, hydrostatic=False, k_split=1, ke_bg=0.0, kord_mt=9,
     kord_tm=-9, kord_tr=9, kord_wz=9, n_split=1, nord=3, p_fac=0.05, rf_fast=True, rf_cutoff=3000.0, tau=10.0,
     vtdm4=0.06, z_tracer=True, do_qa=True, n_sponge=48,
+    # the stock file's saturation-adjustment values (:78-87); used when do_sat_adj=True (the stock setting)
+    tau_i2s=1000.0, tau_g2v=1200.0, ql_gen=0.001, ql_mlt=0.002, qs_mlt=0.000001, qi_lim=1.0, dw_ocean=0.1, dw_land=0.15,
+    icloud_f=0, tau_l2v=300.0, tau_v2l=90.0, fv_sg_adj=0,
 )
 
 

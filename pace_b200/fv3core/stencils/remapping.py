@@ -20,13 +20,27 @@ class LagrangianToEulerian:
             raise NotImplementedError("map ppm, untested mode where kord_tm >= 0")
         if config.hydrostatic:
             raise NotImplementedError("Hydrostatic is not implemented")
-        if config.do_sat_adj:
-            raise NotImplementedError("do_sat_adj=True (SatAdjust3d) is not implemented yet; SURVEY.md §8f row 1")
         for k in (abs(config.kord_tm), abs(config.kord_tr), config.kord_wz, config.kord_mt):
             if k != 9:
                 raise NotImplementedError("only kord 9 is implemented")
         self._rt = rt = stencil_factory.runtime
         self._checkpointer = checkpointer
+        self._do_sat_adjust = bool(config.do_sat_adj)
+        # first level whose reference pressure exceeds 10 hPa (remapping.py:344-348)
+        nz = rt.comm.geometry.nz
+        pf = pfull if pfull is not None else rt.grid_data.p
+        pf = getattr(pf, "data", pf)
+        pf = pf.detach().cpu().numpy() if isinstance(pf, torch.Tensor) else np.asarray(pf)
+        pf = np.asarray(pf, dtype=np.float64).reshape(-1)[:nz]
+        self.kmp = nz - 1
+        for k in range(nz):
+            if pf[k] > 10.0e2:
+                self.kmp = k
+                break
+        if self._do_sat_adjust:
+            from .saturation_adjustment import SatAdjust3d
+
+            self._saturation_adjustment = SatAdjust3d(stencil_factory, config.sat_adjust, area_64, self.kmp)
         self._t_min = 184.0
         self._nq = int(nq)
         self._fill = bool(config.fill)
@@ -83,4 +97,9 @@ class LagrangianToEulerian:
                 raise NotImplementedError("We do not support consv_te > 0.001 because that would trigger an allReduce")
             elif consv_te < -CONSV_MIN:
                 raise NotImplementedError(f"Unimplemented/untested case consv({consv_te})  < -CONSV_MIN({-CONSV_MIN})")
+        if self._do_sat_adjust:
+            fast_mp_consv = consv_te > CONSV_MIN
+            self._saturation_adjustment(dp1, tracers["qvapor"], tracers["qliquid"], tracers["qice"], tracers["qrain"],
+                                        tracers["qsnow"], tracers["qgraupel"], q_cld, hs, peln, delp, delz, q_con, pt, pkz,
+                                        cappa, zvir, mdt, fast_mp_consv, last_step, akap, self.kmp)
         rt.call("fv3_remap_finish", t6, self._pe2.ptr, pe.ptr, pt.ptr, pkz.ptr, int(bool(last_step)), dtmp, float(zvir))

@@ -91,7 +91,43 @@ def c24L2():
     print(inp, f"{size(inp):.1f} MB;", dst, f"{size(dst):.1f} MB")
 
 
+def c12_sat():
+    """do_sat_adj=True (row f1): the stock baroclinic_c12.yaml (`c12sat`, k_split = n_split = 1, qvapor only) and a
+    k_split = 2 run with 8 non-zero tracers (`c12satk2`: both last_step branches, every phase-change branch that
+    condensate can take), plus the SatAdjust3d call snapshots of rank 0 for the stage test."""
+    import sys
+
+    sys.path.insert(0, HERE)
+    from make_committed import reduce_stage
+
+    inp = os.path.join(HERE, "c12_step")
+    for case in ("c12sat", "c12satk2"):
+        src, dst = os.path.join(CACHE, case), os.path.join(HERE, case + "_step")
+        if not os.path.exists(os.path.join(src, "meta.json")):
+            continue
+        os.makedirs(dst, exist_ok=True)
+        meta = json.load(open(os.path.join(src, "meta.json")))
+        for r in range(6):
+            a, b = np.load(os.path.join(inp, f"state0_rank{r}.npz")), np.load(os.path.join(src, f"state0_rank{r}.npz"))
+            for k in b.files:
+                if meta.get("fill_tracers") and k in TRACERS[1:]:
+                    continue
+                assert np.array_equal(a[k], b[k], equal_nan=True), (case, r, k)
+        meta.update(inputs="c12_step", fields=FIELDS + ["qcld"], ranks=[0, 3], levels=None)
+        json.dump(meta, open(os.path.join(dst, "meta.json"), "w"), indent=1, default=str)
+        for r in (0, 3):
+            z = np.load(os.path.join(src, f"state1_rank{r}.npz"))
+            np.savez_compressed(os.path.join(dst, f"state1_rank{r}.npz"), **{n: z[n] for n in FIELDS + ["qcld"]})
+        sd = os.path.join(dst, "stage_rank0")
+        os.makedirs(sd, exist_ok=True)
+        for f in sorted(os.listdir(os.path.join(src, "stage_rank0"))):
+            if f.startswith("SatAdjust3d"):
+                reduce_stage(os.path.join(src, "stage_rank0", f), os.path.join(sd, f))
+        print(dst, f"{sum(os.path.getsize(os.path.join(dp, f)) for dp, _, fs in os.walk(dst) for f in fs) / 1e6:.1f} MB")
+
+
 if __name__ == "__main__":
+    c12_sat()
     if os.path.exists(os.path.join(CACHE, "c12k2n6", "meta.json")):
         c12k2n6()
     if os.path.exists(os.path.join(CACHE, "c24L2k2n3", "meta.json")):

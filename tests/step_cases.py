@@ -30,6 +30,9 @@ CASES = {
     "c12k2n6": dict(dir="c12k2n6_step", substeps=12),
     "c24L2": dict(dir="c24L2_step", inputs="c24L2_inputs", substeps=1),
     "c24L2k2n3": dict(dir="c24L2k2n3_step", substeps=6),
+    # do_sat_adj = True: the stock baroclinic_c12.yaml, and k_split = 2 with 8 non-zero tracers
+    "c12sat": dict(dir="c12sat_step", substeps=1),
+    "c12satk2": dict(dir="c12satk2_step", substeps=2),
 }
 
 
@@ -80,7 +83,8 @@ def build(meta, grids, s0, dev=None, process_comm=None):
         s0 = [s0[r] for r in comm.local_ranks]
     gd = GridData.from_arrays(qf, grids)
     damp = DampingCoefficients.from_arrays(qf, grids)
-    cfg = baroclinic_config(nx, (layout, layout), n_split=meta.get("n_split", 1), k_split=meta.get("k_split", 1))
+    cfg = baroclinic_config(nx, (layout, layout), n_split=meta.get("n_split", 1), k_split=meta.get("k_split", 1),
+                            do_sat_adj=bool(meta.get("do_sat_adj", False)))
     rt = Runtime(comm, qf, gd, damp, cfg)
     sf = StencilFactory(None, GridIndexing.from_sizer_and_communicator(qf.sizer, comm), rt)
     state = DycoreState.init_from_numpy_arrays(s0, qf)
