@@ -165,6 +165,49 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def parity_block(device):
+    """Strict one-timestep parity of the benchmarked split (c12 L79, k_split=2, n_split=6, 8 non-zero tracers) against the
+    reference's final state (tests/step_cases.py, fixtures tests/golden/c12k2n6_step): the achieved worst relative error
+    (over the points above the absolute floor) and worst absolute error per prognostic field, measured on this GPU."""
+    try:
+        from tests import step_cases as S
+
+        if not S.available("c12k2n6"):
+            return {"case": "c12k2n6", "status": "fixtures not present"}
+        meta, grids, s0, s1 = S.load("c12k2n6")
+        dycore, state = S.build(meta, grids, s0, device)
+        dycore.step_dynamics(state)
+        import torch
+
+        torch.cuda.synchronize()
+        failures, achieved = S.compare(state.as_numpy(), s1, meta)
+        return {"case": "c12 L79 layout (1,1), k_split=2, n_split=6, 8 non-zero tracers, reference = unmodified ai2cm/pace numpy backend",
+                "status": "pass" if not failures else f"{len(failures)} failures", "tolerance": "relative 1e-10 or the reference's calibrated floors",
+                "worst_rel": {k: v[0] for k, v in achieved.items()}, "worst_abs": {k: v[1] for k, v in achieved.items()}}
+    except Exception as exc:  # the bench line must not die on the side check
+        return {"case": "c12k2n6", "status": f"not run: {exc!r}"}
+
+
+def fp64_peak_tflops(lib, device):
+    """Measured fp64 FMA throughput of this GPU (fv3_fp64_peak: 8 independent FMA chains per thread on every SM): the
+    instruction roof of the plane / column kernels, which ncu shows to be issue- and fp64-bound rather than HBM-bound."""
+    import torch
+
+    blocks, iters = 148 * 16, 20000
+    out = torch.empty(blocks * 128, dtype=torch.float64, device=device)
+    st = torch.cuda.current_stream().cuda_stream
+    best = None
+    for _ in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        lib.fv3_fp64_peak(out.data_ptr(), iters, blocks, st)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None else min(best, ms)
+    return 2.0 * 8 * iters * 128 * blocks / (best / 1e3) / 1e12
+
+
 def workload_config(args):
     return {
         "workload": f"C{args.nx} L79 baroclinic (Jablonowski-Williamson), layout ({args.layout},{args.layout}) = "
@@ -229,6 +272,8 @@ def main():
         torch.cuda.synchronize()
 
     lib = _lib.load()
+    parity = parity_block(device) if rank == 0 else None
+    fp64_peak = fp64_peak_tflops(lib, device) if rank == 0 else None
     dycore, state, comm, rt, gd = build_dycore(args.nx, args.layout, 79, args.k_split, args.n_split, device, pc)
     n_local = comm.geometry.n_sub
     cells_local = n_local * comm.geometry.nx * comm.geometry.ny * 79
@@ -372,11 +417,21 @@ def main():
         t_ms, n, name = dom
         bytes_per_launch = STAGE_PASSES[name] * 8 * cells_local
         achieved = bytes_per_launch / (t_ms / n / 1e3) / 1e9
-        traffic = None
+        traffic, fp64 = None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get(name)
+            tj = json.load(open(tp))
+            traffic = tj.get(name)
+            # fp64 roof of the same stage: DADD + DMUL + 2 x DFMA thread-instructions per call from the same ncu pass
+            # (C128, all 24 subdomains), scaled to the cells this rank owns
+            ops = tj.get("_fp64_flops", {}).get(name)
+            if ops and fp64_peak:
+                flops = ops * cells_local / (6 * args.nx * args.nx * 79)
+                fp64 = {"flops_per_launch": flops, "achieved_tflops": flops / (t_ms / n / 1e3) / 1e12, "peak_tflops": fp64_peak,
+                        "frac": flops / (t_ms / n / 1e3) / 1e12 / fp64_peak,
+                        "peak_source": "measured in this run (fv3_fp64_peak, 8 independent FMA chains per thread)"}
         roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "fp64": fp64, "binding_roof": ("fp64" if fp64 and fp64["frac"] > achieved / peak else "hbm"),
                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
                     "avg_launch_ms": t_ms / n, "share_of_step": t_ms / (ms_eager * n_eager),
                     "step_achieved_GBps": algorithmic_bytes_per_cell(args.k_split, args.n_split) * cells_total / (ms / 1e3) / 1e9,
@@ -398,7 +453,8 @@ def main():
         "metric": "C128L79 baroclinic dycore s/timestep", "value": ms / 1e3, "unit": "s/timestep", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args), "clocks": clocks,
-        "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "finite": finite, "state_digest": digest,
+        "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "fp64_peak_tflops": fp64_peak, "finite": finite,
+        "state_digest": digest,
         "launch_mode": mode, "ms_per_step_eager": ms_eager, "host_enqueue_ms_per_step": host_enqueue_ms,
     }
     print(json.dumps(line), flush=True)

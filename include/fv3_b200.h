@@ -102,6 +102,9 @@ int fv3_abi_version(void);
 int fv3_is_hostsim(void);
 /* CUDA kernels launched by this library since it was loaded (bench.py reports the difference over the timed region) */
 int64_t fv3_launch_count(void);
+/* measurement aid: blocks x 128 threads run iters x 8 independent fp64 FMAs each (2 * 8 * iters * 128 * blocks flops);
+ * out: blocks * 128 doubles.  bench.py times it to get the fp64 roof of this GPU. */
+int fv3_fp64_peak(double *out, int iters, int blocks, void *stream);
 /* number of 3-D scratch fields fv3_create needs (scratch_bytes >= n * ss * n_sub * 8) */
 int fv3_scratch_fields(void);
 

@@ -119,13 +119,14 @@ FV_HD double a2b_edge_value(const fv3_geom &g, const fv3_grid &m, int s, Q q, in
 // On return OUT holds the corner rows [ja, jb] of the strip.
 template <class B>
 FV_DEV void a2b_plane(const fv3_geom &g, const fv3_grid &m, int s, const B &b, const double *qin, double *SQ, double *QX,
-                     double *QY, double *OUT) {
+                     double *QY, double *OUT, bool loaded = false) {
   const int sj = g.sj, h = g.halo;
   const int isc = h, iec = h + g.nx - 1, jsc = h, jec = h + g.ny - 1;
   const bool W = on_west(g, s), E = on_east(g, s), S = on_south(g, s), N = on_north(g, s);
   const int nwi = g.ni - 1, nwj = g.nj - 1;
   const int ja = b.ja, jb = b.jb;
-  b.rect(0, nwi, b.lo(0, h), b.hi(nwj, h), [&](int i, int j) { SQ[j * sj + i] = qin[j * sj + i]; });
+  // loaded: SQ already holds qin on every resident row (the caller produced it in shared memory)
+  if (!loaded) b.rect(0, nwi, b.lo(0, h), b.hi(nwj, h), [&](int i, int j) { SQ[j * sj + i] = qin[j * sj + i]; });
   auto q = [&](int ii, int jj) { return SQ[jj * sj + ii]; };
   // qx on corner columns isc..iec+1, rows ja-2..jb+1; qy on rows ja..jb, columns isc-2..iec+2
   // (a last strip of ONE row on a north tile edge: its row jec reads qx three rows down, a2b_ord4.py:286-311)

@@ -62,4 +62,28 @@ fv3_ctx *fv3_create(const fv3_geom *geom, const fv3_config *config, const fv3_gr
 
 void fv3_destroy(fv3_ctx *ctx) { delete ctx; }
 
+// Measurement aid (bench.py): a dependent-chain-free stream of fp64 FMAs on every SM, `chains` independent accumulators
+// per thread.  2 * iters * chains * threads flops per launch; out receives one value per thread so that nothing is
+// optimised away.  Gives the fp64 roof the plane / column kernels are compared with (they are instruction-bound, not
+// HBM-bound).
+int fv3_fp64_peak(double *out, int iters, int blocks, void *stream) {
+#ifdef FV3_HOSTSIM
+  (void)out; (void)iters; (void)blocks; (void)stream;
+  return 0;
+#else
+  fv3::launch1d((cudaStream_t)stream, (int64_t)blocks * 128, 1, 1, FV_LAMBDA(int64_t e, int, int) {
+    double a0 = 1.0 + 1e-9 * (double)e, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0, a4 = a0 + 4.0, a5 = a0 + 5.0,
+           a6 = a0 + 6.0, a7 = a0 + 7.0;
+    const double m = 1.0 - 1e-12, c = 1e-13;
+#pragma unroll 4
+    for (int i = 0; i < iters; ++i) {
+      a0 = __fma_rn(a0, m, c); a1 = __fma_rn(a1, m, c); a2 = __fma_rn(a2, m, c); a3 = __fma_rn(a3, m, c);
+      a4 = __fma_rn(a4, m, c); a5 = __fma_rn(a5, m, c); a6 = __fma_rn(a6, m, c); a7 = __fma_rn(a7, m, c);
+    }
+    out[e] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  });
+  return fv3::check_launch("fv3_fp64_peak");
+#endif
+}
+
 }  // extern "C"

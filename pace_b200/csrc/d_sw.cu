@@ -270,6 +270,325 @@ FV_HD double advect_along(int mord, Q q, DXE dxe, Z zero, double ub, double cfl,
 }
 
 
+// kinetic energy at the cell corner (i, j) (d_sw.py:204-298): winds advected along their own direction to the corner
+// (xtp_u.py / ytp_v.py), edge and corner forms next to the cube-tile edges
+FV_DEV double ke_point(const fv3_geom &g, const fv3_grid &m, int s, int i, int j, int k, const double *u, const double *v,
+                      const double *uc, const double *vc, const double *ucc, const double *vcc, double dt, int mord) {
+  const int isc = g.halo, iec = g.halo + g.nx - 1, jsc = g.halo, jec = g.halo + g.ny - 1, sj = g.sj;
+    const bool W = fv3::on_west(g, s), E = fv3::on_east(g, s), S = fv3::on_south(g, s), N = fv3::on_north(g, s);
+    const int64_t o = O3(s, i, j, k), o2 = O2(s, i, j);
+    const bool ie_ = (W && i == isc) || (E && i == iec + 1), je_ = (S && j == jsc) || (N && j == jec + 1);
+    const double ub_cov = 0.5 * (uc[o - sj] + uc[o]), vb_cov = 0.5 * (vc[o - 1] + vc[o]);
+    double ub = (ub_cov - vb_cov * m.cosa[o2]) * m.rsina[o2];
+    double vb = (vb_cov - ub_cov * m.cosa[o2]) * m.rsina[o2];
+    if (je_) ub = 0.25 * (-ucc[o - 2 * sj] + 3.0 * (ucc[o - sj] + ucc[o]) - ucc[o + sj]);
+    if (ie_) ub = 0.5 * (ucc[o - sj] + ucc[o]);
+    if (ie_) vb = 0.25 * (-vcc[o - 2] + 3.0 * (vcc[o - 1] + vcc[o]) - vcc[o + 1]);
+    if (je_) vb = 0.5 * (vcc[o - 1] + vcc[o]);
+    double kev;
+    if (ie_ && je_) {
+      // corner_ke (d_sw.py:258-283)
+      int io1, jo1, io2;
+      double vsign;
+      if (i == isc && j == jsc) { io1 = 0; jo1 = 0; io2 = -1; vsign = 1; }
+      else if (i != isc && j == jsc) { io1 = -1; jo1 = 0; io2 = 0; vsign = -1; }
+      else if (i != isc && j != jsc) { io1 = -1; jo1 = -1; io2 = 0; vsign = 1; }
+      else { io1 = 0; jo1 = -1; io2 = -1; vsign = -1; }
+      const double dt6 = dt / 6.0;
+      const double u0 = u[o], um = u[o - 1], v0 = v[o], vm = v[o - sj];
+      const double ut0 = ucc[o], utm = ucc[o - sj], vt0 = vcc[o], vtm = vcc[o - 1];
+      kev = dt6 * ((ut0 + utm) * ((io1 + 1) * u0 - (io1 * um)) + (vt0 + vtm) * ((jo1 + 1) * v0 - (jo1 * vm)) +
+                   (((jo1 + 1) * ut0 - (jo1 * utm)) + vsign * ((io1 + 1) * vt0 - (io1 * vtm))) * ((io2 + 1) * u0 - (io2 * um)));
+    } else if (!((W && i <= isc + 3) || (E && i >= iec - 2) || (S && j <= jsc + 3) || (N && j >= jec - 2))) {
+      // away from the tile edges: interior edge values, no zeroed parabolas (same expressions as advect_along)
+      auto adv = [&](const double *q, int64_t st, double ubv, double cfl) {
+        const double qm2 = q[-2 * st], ql = q[-st], qr = q[0], qp1 = q[st];
+        const double al0 = fv3::PPM_P1 * (qm2 + ql) + fv3::PPM_P2 * (q[-3 * st] + qr);
+        const double al1 = fv3::PPM_P1 * (ql + qr) + fv3::PPM_P2 * (qm2 + qp1);
+        const double al2 = fv3::PPM_P1 * (qr + qp1) + fv3::PPM_P2 * (ql + q[2 * st]);
+        const double bl_l = al0 - ql, br_l = al1 - ql, bl_r = al1 - qr, br_r = al2 - qr;
+        const double b0_l = bl_l + br_l, b0_r = bl_r + br_r;
+        const double fx0 = fv3::ppm_fx1(cfl, br_l, b0_l, bl_r, b0_r);
+        bool s_l, s_r;
+        if (mord == 5) {
+          s_l = bl_l * br_l < 0;
+          s_r = bl_r * br_r < 0;
+        } else {
+          s_l = (3.0 * fabs(b0_l)) < fabs(bl_l - br_l);
+          s_r = (3.0 * fabs(b0_r)) < fabs(bl_r - br_r);
+        }
+        const double mask = (s_l || s_r) ? 1.0 : 0.0;
+        return ubv > 0.0 ? ql + fx0 * mask : qr + fx0 * mask;
+      };
+      const double cflx = ub > 0 ? ub * dt * m.rdx[o2 - 1] : ub * dt * m.rdx[o2];
+      const double cfly = vb > 0 ? vb * dt * m.rdy[o2 - sj] : vb * dt * m.rdy[o2];
+      kev = 0.5 * dt * (ub * adv(u + o, 1, ub, cflx) + vb * adv(v + o, sj, vb, cfly));
+    } else {
+      const fv3::Edge1D ex{W, E, isc, iec}, ey{S, N, jsc, jec};
+      auto qu = [&](int ii) { return u[O3(s, ii, j, k)]; };
+      auto dxe = [&](int ii) { return m.dx[O2(s, ii, j)]; };
+      auto zx = [&](int ii) { return je_ && ((W && (ii == isc - 1 || ii == isc)) || (E && (ii == iec || ii == iec + 1))); };
+      const double cflx = ub > 0 ? ub * dt * m.rdx[o2 - 1] : ub * dt * m.rdx[o2];
+      const double adv_u = advect_along(mord, qu, dxe, zx, ub, cflx, i, ex);
+      auto qv = [&](int jj) { return v[O3(s, i, jj, k)]; };
+      auto dye = [&](int jj) { return m.dy[O2(s, i, jj)]; };
+      auto zy = [&](int jj) { return ie_ && ((S && (jj == jsc - 1 || jj == jsc)) || (N && (jj == jec || jj == jec + 1))); };
+      const double cfly = vb > 0 ? vb * dt * m.rdy[o2 - sj] : vb * dt * m.rdy[o2];
+      const double adv_v = advect_along(mord, qv, dye, zy, vb, cfly, j, ey);
+      kev = 0.5 * dt * (ub * adv_u + vb * adv_v);
+    }
+    return kev;
+}
+
+// ---- plane forms of the divergence-damping pieces, used by the fused momentum stage -----------------------------------
+// second-order damping divergence of the sponge levels at corner (i, j) (divergence_damping.py:21-118)
+FV_DEV double div2_point(const fv3_geom &g, const fv3_grid &m, int s, int i, int j, int k, const double *u, const double *v,
+                        const double *ua, const double *va, const double *uc, const double *vc) {
+  const int isc = g.halo, iec = g.halo + g.nx - 1, jsc = g.halo, jec = g.halo + g.ny - 1, sj = g.sj;
+  const bool W = fv3::on_west(g, s), E = fv3::on_east(g, s), S = fv3::on_south(g, s), N = fv3::on_north(g, s);
+  auto ucd = [&](int ii, int jj) {  // u_contra * dyc at (x centre, y interface)
+    const int64_t o = O3(s, ii, jj, k), o2 = O2(s, ii, jj);
+    double uco;
+    if ((S && jj == jsc) || (N && jj == jec + 1))
+      uco = vc[o] > 0 ? u[o] * m.sin_sg4[o2 - sj] : u[o] * m.sin_sg2[o2];
+    else
+      uco = (u[o] - 0.5 * (va[o - sj] + va[o]) * m.cosa_v[o2]) * m.sina_v[o2];
+    return uco * m.dyc[o2];
+  };
+  auto vcd = [&](int ii, int jj) {
+    const int64_t o = O3(s, ii, jj, k), o2 = O2(s, ii, jj);
+    double vco;
+    if ((W && ii == isc) || (E && ii == iec + 1))
+      vco = uc[o] > 0 ? v[o] * m.sin_sg3[o2 - 1] : v[o] * m.sin_sg1[o2];
+    else
+      vco = (v[o] - 0.5 * (ua[o - 1] + ua[o]) * m.cosa_u[o2]) * m.sina_u[o2];
+    return vco * m.dxc[o2];
+  };
+  const double vm = vcd(i, j - 1), v0 = vcd(i, j), um = ucd(i - 1, j), u0 = ucd(i, j);
+  double d = vm - v0 + um - u0;
+  const bool ci = (W && i == isc) || (E && i == iec + 1);
+  if (ci && S && j == jsc) d = d - vm;
+  if (ci && N && j == jec + 1) d = d + v0;
+  return m.rarea_c[O2(s, i, j)] * d;
+}
+
+// one Laplacian iteration of the divergence damping (divergence_damping.py:566-589) on shared planes: DST <- rarea_c *
+// div(grad(SRC) scaled by divg_u / divg_v) on corners [isc-nt, iec+nt+1] x [j0, j1), cube-corner fills as read remaps
+FV_DEV void divg_iter_plane(const fv3_geom &g, const fv3_grid &m, int s, const fv3::Block &b, const double *SRC, double *DST,
+                           int nt, bool fillc, int j0, int j1) {
+  const int isc = g.halo, iec = g.halo + g.nx - 1, jsc = g.halo, jec = g.halo + g.ny - 1, sj = g.sj;
+  const bool W = fv3::on_west(g, s), E = fv3::on_east(g, s), S = fv3::on_south(g, s), N = fv3::on_north(g, s);
+  const int64_t o2b = O2(s, 0, 0);
+  const double *divg_u = m.divg_u + o2b, *divg_v = m.divg_v + o2b, *rarea_c = m.rarea_c + o2b;
+  b.rect(isc - nt, iec + nt + 2, j0, j1, [&](int i, int j) {
+    const int p = j * sj + i;
+    if (!((W || E) && (S || N) && (i <= isc + 2 || i >= iec - 1) && (j <= jsc + 2 || j >= jec - 1))) {
+      const double dc = SRC[p];
+      const double ucm = (dc - SRC[p - sj]) * divg_v[p - sj], uc0 = (SRC[p + sj] - dc) * divg_v[p];
+      const double vcm = (dc - SRC[p - 1]) * divg_u[p - 1], vc0 = (SRC[p + 1] - dc) * divg_u[p];
+      DST[p] = (ucm - uc0 + vcm - vc0) * rarea_c[p];
+      return;
+    }
+    auto dgx = [&](int ii, int jj) {
+      if (fillc) bgrid_corner_x(g, s, ii, jj);
+      return SRC[jj * sj + ii];
+    };
+    auto dgy = [&](int ii, int jj) {
+      if (fillc) bgrid_corner_y(g, s, ii, jj);
+      return SRC[jj * sj + ii];
+    };
+    auto vc_raw = [&](int ii, int jj) { return (dgx(ii + 1, jj) - dgx(ii, jj)) * divg_u[jj * sj + ii]; };
+    auto uc_raw = [&](int ii, int jj) { return (dgy(ii, jj + 1) - dgy(ii, jj)) * divg_v[jj * sj + ii]; };
+    auto vc_at = [&](int ii, int jj) {
+      if (fillc) {
+        const bool xo_w = ii < isc, xo_e = ii > iec, yo_s = jj < jsc, yo_n = jj > jec + 1;
+        if ((xo_w || xo_e) && (yo_s || yo_n) && (xo_w ? W : E) && (yo_s ? S : N)) {
+          const int a = xo_w ? isc - ii : ii - iec, bb = yo_s ? jsc - jj : jj - (jec + 1);
+          const double sg = (xo_w == yo_s) ? -1.0 : 1.0;
+          const int si = xo_w ? isc - bb : iec + 1 + bb;
+          const int sjj = yo_s ? jsc + a - 1 : jec + 1 - a;
+          return sg * uc_raw(si, sjj);
+        }
+      }
+      return vc_raw(ii, jj);
+    };
+    auto uc_at = [&](int ii, int jj) {
+      if (fillc) {
+        const bool xo_w = ii < isc, xo_e = ii > iec + 1, yo_s = jj < jsc, yo_n = jj > jec;
+        if ((xo_w || xo_e) && (yo_s || yo_n) && (xo_w ? W : E) && (yo_s ? S : N)) {
+          const int a = xo_w ? isc - ii : ii - (iec + 1), bb = yo_s ? jsc - jj : jj - jec;
+          const double sg = (xo_w == yo_s) ? -1.0 : 1.0;
+          const int si = xo_w ? isc + bb - 1 : iec + 1 - bb;
+          const int sjj = yo_s ? jsc - a : jec + 1 + a;
+          return sg * vc_raw(si, sjj);
+        }
+      }
+      return uc_raw(ii, jj);
+    };
+    const double ucm = uc_at(i, j - 1), uc0 = uc_at(i, j), vcm = vc_at(i - 1, j), vc0 = vc_at(i, j);
+    double d = ucm - uc0 + vcm - vc0;
+    const bool ci = (W && i == isc) || (E && i == iec + 1);
+    if (ci && S && j == jsc) d = d - ucm;
+    if (ci && N && j == jec + 1) d = d + uc0;
+    DST[p] = d * rarea_c[p];
+  });
+}
+
+// ---- K3a: kinetic energy, relative vorticity and the divergence damping of d_sw (d_sw.py:204-328,
+// divergence_damping.py:482-632), ONE strip-resident kernel.  The relative vorticity plane, the Laplacian iterates of
+// the divergence and the three A->B interpolation temporaries live in shared memory; written: ke (+ damping), the
+// damped B-grid vorticity, and the A-grid vorticity (read again by K3b's transport and del-n damping).  delpc and
+// divg_d are scratch in the reference after this point (nothing downstream reads them) and are not written.
+int dsw_vorticity_launch(fv3_ctx *ctx, cudaStream_t st, const double *u, const double *v, const double *ua, const double *va,
+                         const double *uc, const double *vc, const double *ucc, const double *vcc, const double *divgd,
+                         double *ke, double *vort_a, double *vort_b, double dt, const fv3_dsw_cols *c) {
+  const fv3_geom g = ctx->g;
+  const fv3_grid m = ctx->m;
+  const fv3_config cfg = ctx->c;
+  const int k0 = c->nonzero_nord_k, nord = c->nonzero_nord;
+  const double da_min_c = cfg.da_min_c, dddmp = cfg.dddmp;
+  const double *d2_bg = c->d2_divg;
+  const int mord = cfg.hord_mt < 0 ? -cfg.hord_mt : cfg.hord_mt;
+  const double absdt = fabs(dt);
+  const double dd8 = pow(da_min_c * cfg.d4_bg, (double)(nord + 1));
+  return fv3::launch_planes(ctx, st, 0, g.nz, 5, FV_LAMBDA(int s, int k, const fv3::Block &b) { FV_DEV_GM
+    double *VA = b.plane(0), *DF = b.plane(1), *QX = b.plane(2), *QY = b.plane(3), *OUT = b.plane(4);
+    const int sj = g.sj, h = g.halo;
+    const int isc = h, iec = h + g.nx - 1, jsc = h, jec = h + g.ny - 1, ied = iec + h, jed = jec + h;
+    const int ja = b.ja, jt = b.jtop();
+    const int64_t ob = O3(s, 0, 0, k), o2b = O2(s, 0, 0);
+    const bool sponge = k < k0;
+    if (!sponge && nord > 0) {  // the divergence of the previous C-grid step: start its transfer now
+      b.bulk_begin(1, sj);
+      b.bulk_rows(QX, divgd + ob, sj);
+    }
+    // relative vorticity on the A grid (d_sw.py:301-328) on every resident row; stored for the rows this strip owns
+    {
+      const double *dxm = m.dx + o2b, *dym = m.dy + o2b, *rarea = m.rarea + o2b;
+      const double *up = u + ob, *vp = v + ob;
+      const int jlo = b.first ? 0 : ja, jhi = b.last ? jed + 1 : b.jb;
+      b.rect(0, ied + 1, b.lo(0, h), b.hi(jed + 1, h), [&](int i, int j) {
+        const int p = j * sj + i;
+        const double rdy_tmp = rarea[p] * dxm[p], rdx_tmp = rarea[p] * dym[p];
+        const double vo = (up[p] - up[p + sj] * dxm[p + sj] / dxm[p]) * rdy_tmp + (vp[p + 1] * dym[p + 1] / dym[p] - vp[p]) * rdx_tmp;
+        VA[p] = vo;
+        if (j >= jlo && j < jhi) vort_a[ob + p] = vo;
+      });
+    }
+    const bool smag = !(dddmp < 1e-5);
+    if (!sponge) {
+      // nord Laplacian iterations of the divergence (divergence_damping.py:566-589), ping-pong between the planes the
+      // A->B interpolation uses afterwards; the last iterate lands in DF
+      if (nord > 0) b.bulk_wait();
+      const double *src = QX;
+      for (int n = 0; n < nord; ++n) {
+        const int nt = nord - (n + 1);
+        double *dst = (n + 1 == nord) ? DF : (src == QX ? QY : QX);
+        divg_iter_plane(g, m, s, b, src, dst, nt, n + 1 != nord, b.lo(jsc - nt, nt), b.hi(jec + nt + 2, nt + 1));
+        src = dst;
+      }
+      if (smag) fv3::a2b_plane(g, m, s, b, vort_a + ob, VA, QX, QY, OUT, true);
+    }
+    // damping term and kinetic energy on the corners this strip owns
+    b.rect(isc, iec + 2, ja, jt + 1, [&](int i, int j) {
+      const int p = j * sj + i;
+      const int64_t o = ob + p;
+      double vo;
+      if (sponge) {
+        const double d = div2_point(g, m, s, i, j, k, u, v, ua, va, uc, vc);
+        const double damp = da_min_c * fv3::dmax(d2_bg[k], fv3::dmin(0.2, dddmp * fabs(d * dt)));
+        vo = damp * d;
+      } else {
+        const double dp = divgd[o];
+        double vo0 = 0.0;
+        if (smag) {
+          const double vb = OUT[p];
+          vo0 = absdt * sqrt(dp * dp + vb * vb);
+        }
+        const double damp = da_min_c * fv3::dmax(d2_bg[k], fv3::dmin(0.2, dddmp * fabs(vo0)));
+        vo = damp * dp + dd8 * (nord > 0 ? DF[p] : dp);
+      }
+      vort_b[o] = vo;
+      ke[o] = ke_point(g, m, s, i, j, k, u, v, uc, vc, ucc, vcc, dt, mord) + vo;
+    });
+  });
+}
+
+// ---- K3b: absolute-vorticity transport, wind update from the kinetic-energy gradient and the vorticity flux, del-n
+// damping of the vorticity, the heat it dissipates, final winds (d_sw.py:1131-1237), ONE strip-resident kernel.
+// u's first row of every strip but the first is parked (the strip below still reads the old value), see unpark below.
+template <int MORD>
+int dsw_winds_launch(fv3_ctx *ctx, cudaStream_t st, double *u, double *v, const double *ke, const double *vort_a,
+                     const double *vort_b, const double *crx, const double *cry, const double *xfx, const double *yfx,
+                     const double *delp, const double *heat_s, double *heat_source, double *side_u, double dt,
+                     const fv3_dsw_cols *c) {
+  const fv3_geom g = ctx->g;
+  const fv3_grid m = ctx->m;
+  const fv3_config cfg = ctx->c;
+  const fv3_dsw_cols cl = *c;
+  const double d_con_cfg = cfg.d_con;
+  return fv3::launch_planes(ctx, st, 0, g.nz, fv3::FVTP_PLANES, FV_LAMBDA(int s, int k, const fv3::Block &b) { FV_DEV_GM
+    double *Q = b.plane(0), *A = b.plane(1), *B = b.plane(2), *D = b.plane(3), *T = b.plane(4);
+    const int sj = g.sj, h = g.halo, nx = g.nx;
+    const int isc = h, iec = h + nx - 1;
+    const int ja = b.ja, jb = b.jb, jt = b.jtop();
+    const int64_t ob = O3(s, 0, 0, k), o2b = O2(s, 0, 0);
+    const double *dxm = m.dx + o2b, *dym = m.dy + o2b, *rdx = m.rdx + o2b, *rdy = m.rdy + o2b;
+    // absolute vorticity = relative vorticity + f0, transported with the area fluxes (d_sw.py:1131-1147)
+    fv3::PlaneArgs pa{vort_a, crx, cry, xfx, yfx, xfx, yfx};
+    pa.add2d = m.f0 + o2b;
+    fv3::fvtp2d_plane<MORD, true>(g, m, s, k, b, pa, Q, A, B, D, T);
+    // u_and_v_from_ke (d_sw.py:439-477): u' -> Q on faces [ja, jb], v' -> D on rows [ja, jb)
+    {
+      const double *kp = ke + ob, *up = u + ob, *vp = v + ob;
+      b.rect(isc, iec + 2, ja, jb + 1, [&](int i, int j) {
+        const int p = j * sj + i;
+        if (i <= iec) Q[p] = up[p] * dxm[p] + kp[p] - kp[p + 1] + A[p];
+        if (j < jb) D[p] = vp[p] * dym[p] + kp[p] - kp[p + sj] - B[p];
+      });
+    }
+    // del-n damping fluxes of the relative vorticity (d_sw.py:1160-1166): fx2 -> A ("ut"), fy2 -> B ("vt")
+    fv3::delnflux_plane(g, m, s, b, vort_a + ob, cl.dn_damp_vt_c[k], cl.nord_v[k] > 0, cl.nmax_v, false, T, A, B);
+    // vort_differencing + heat_source_from_vorticity_damping (d_sw.py:349-577) on the cells this strip owns
+    {
+      const bool dc = cl.d_con[k] > DCON_THRESHOLD;
+      const double dcon_k = cl.d_con[k];
+      const double *vb_ = vort_b + ob, *rsin2 = m.rsin2 + o2b, *cosa_s = m.cosa_s + o2b;
+      b.rect(isc, iec + 1, ja, jb, [&](int i, int j) {
+        const int p = j * sj + i;
+        const int64_t o = ob + p;
+        double hs = heat_s[o];
+        if (dc) {
+          auto ubt = [&](int pp) { return ((vb_[pp] - vb_[pp + 1]) + B[pp]) * rdx[pp]; };
+          auto vbt = [&](int pp) { return ((vb_[pp] - vb_[pp + sj]) - A[pp]) * rdy[pp]; };
+          const double ub0 = ubt(p), ub1 = ubt(p + sj), vb0 = vbt(p), vb1 = vbt(p + 1);
+          const double fy0 = Q[p] * rdx[p], fy1 = Q[p + sj] * rdx[p + sj];
+          const double fx0 = D[p] * rdy[p], fx1 = D[p + 1] * rdy[p + 1];
+          const double gy0 = fy0 * ub0, gy1 = fy1 * ub1, gx0 = fx0 * vb0, gx1 = fx1 * vb1;
+          const double u2 = fy0 + fy1, du2 = ub0 + ub1, v2 = fx0 + fx1, dv2 = vb0 + vb1;
+          const double dampterm = rsin2[p] * 0.25 *
+                                  ((ub0 * ub0 + ub1 * ub1 + vb0 * vb0 + vb1 * vb1) + 2.0 * (gy0 + gy1 + gx0 + gx1) -
+                                   cosa_s[p] * (u2 * dv2 + v2 * du2 + du2 * dv2));
+          hs = delp[o] * (hs - dcon_k * dampterm);
+        }
+        if (d_con_cfg > DCON_THRESHOLD) heat_source[o] = heat_source[o] + hs;
+      });
+    }
+    // update_u_and_v (d_sw.py:582-608) and the stores
+    {
+      const bool dv = cl.damp_vt[k] > 1e-5;
+      b.rect(isc, iec + 2, ja, jt + 1, [&](int i, int j) {
+        const int p = j * sj + i;
+        if (i <= iec) {
+          const double un = dv ? Q[p] + B[p] : Q[p];
+          ((j == ja && !b.first) ? side_u : u)[ob + p] = un;
+        }
+        if (j < jb) v[ob + p] = dv ? D[p] - A[p] : D[p];
+      });
+    }
+  });
+}
+
 struct Fields4 {
   double *f[4];
 };
@@ -486,134 +805,38 @@ int fv3_d_sw(fv3_ctx *ctx, double *delpc, double *delp, double *pt, double *u, d
     if (rc) return rc;
   }
   unpark_rows(ctx, st, Fields4{{w, q_con, pt, delp}}, 4, side0, nz);
-  // kinetic energy on cell corners (d_sw.py:204-298)
+  // K3a: kinetic energy, vorticity, divergence damping (d_sw.py:204-328, divergence_damping.py:482-632)
   const int mord = cfg.hord_mt < 0 ? -cfg.hord_mt : cfg.hord_mt;
   if (mord >= 8) {
     fv3::set_error("fv3_d_sw: hord_mt >= 8 is not implemented");
     return -1;
   }
-  fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, 0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
-    const bool W = fv3::on_west(g, s), E = fv3::on_east(g, s), S = fv3::on_south(g, s), N = fv3::on_north(g, s);
-    const int64_t o = O3(s, i, j, k), o2 = O2(s, i, j);
-    const bool ie_ = (W && i == isc) || (E && i == iec + 1), je_ = (S && j == jsc) || (N && j == jec + 1);
-    const double ub_cov = 0.5 * (uc[o - sj] + uc[o]), vb_cov = 0.5 * (vc[o - 1] + vc[o]);
-    double ub = (ub_cov - vb_cov * m.cosa[o2]) * m.rsina[o2];
-    double vb = (vb_cov - ub_cov * m.cosa[o2]) * m.rsina[o2];
-    if (je_) ub = 0.25 * (-ucc[o - 2 * sj] + 3.0 * (ucc[o - sj] + ucc[o]) - ucc[o + sj]);
-    if (ie_) ub = 0.5 * (ucc[o - sj] + ucc[o]);
-    if (ie_) vb = 0.25 * (-vcc[o - 2] + 3.0 * (vcc[o - 1] + vcc[o]) - vcc[o + 1]);
-    if (je_) vb = 0.5 * (vcc[o - 1] + vcc[o]);
-    double kev;
-    if (ie_ && je_) {
-      // corner_ke (d_sw.py:258-283)
-      int io1, jo1, io2;
-      double vsign;
-      if (i == isc && j == jsc) { io1 = 0; jo1 = 0; io2 = -1; vsign = 1; }
-      else if (i != isc && j == jsc) { io1 = -1; jo1 = 0; io2 = 0; vsign = -1; }
-      else if (i != isc && j != jsc) { io1 = -1; jo1 = -1; io2 = 0; vsign = 1; }
-      else { io1 = 0; jo1 = -1; io2 = -1; vsign = -1; }
-      const double dt6 = dt / 6.0;
-      const double u0 = u[o], um = u[o - 1], v0 = v[o], vm = v[o - sj];
-      const double ut0 = ucc[o], utm = ucc[o - sj], vt0 = vcc[o], vtm = vcc[o - 1];
-      kev = dt6 * ((ut0 + utm) * ((io1 + 1) * u0 - (io1 * um)) + (vt0 + vtm) * ((jo1 + 1) * v0 - (jo1 * vm)) +
-                   (((jo1 + 1) * ut0 - (jo1 * utm)) + vsign * ((io1 + 1) * vt0 - (io1 * vtm))) * ((io2 + 1) * u0 - (io2 * um)));
-    } else if (!((W && i <= isc + 3) || (E && i >= iec - 2) || (S && j <= jsc + 3) || (N && j >= jec - 2))) {
-      // away from the tile edges: interior edge values, no zeroed parabolas (same expressions as advect_along)
-      auto adv = [&](const double *q, int64_t st, double ubv, double cfl) {
-        const double qm2 = q[-2 * st], ql = q[-st], qr = q[0], qp1 = q[st];
-        const double al0 = fv3::PPM_P1 * (qm2 + ql) + fv3::PPM_P2 * (q[-3 * st] + qr);
-        const double al1 = fv3::PPM_P1 * (ql + qr) + fv3::PPM_P2 * (qm2 + qp1);
-        const double al2 = fv3::PPM_P1 * (qr + qp1) + fv3::PPM_P2 * (ql + q[2 * st]);
-        const double bl_l = al0 - ql, br_l = al1 - ql, bl_r = al1 - qr, br_r = al2 - qr;
-        const double b0_l = bl_l + br_l, b0_r = bl_r + br_r;
-        const double fx0 = fv3::ppm_fx1(cfl, br_l, b0_l, bl_r, b0_r);
-        bool s_l, s_r;
-        if (mord == 5) {
-          s_l = bl_l * br_l < 0;
-          s_r = bl_r * br_r < 0;
-        } else {
-          s_l = (3.0 * fabs(b0_l)) < fabs(bl_l - br_l);
-          s_r = (3.0 * fabs(b0_r)) < fabs(bl_r - br_r);
-        }
-        const double mask = (s_l || s_r) ? 1.0 : 0.0;
-        return ubv > 0.0 ? ql + fx0 * mask : qr + fx0 * mask;
-      };
-      const double cflx = ub > 0 ? ub * dt * m.rdx[o2 - 1] : ub * dt * m.rdx[o2];
-      const double cfly = vb > 0 ? vb * dt * m.rdy[o2 - sj] : vb * dt * m.rdy[o2];
-      kev = 0.5 * dt * (ub * adv(u + o, 1, ub, cflx) + vb * adv(v + o, sj, vb, cfly));
-    } else {
-      const fv3::Edge1D ex{W, E, isc, iec}, ey{S, N, jsc, jec};
-      auto qu = [&](int ii) { return u[O3(s, ii, j, k)]; };
-      auto dxe = [&](int ii) { return m.dx[O2(s, ii, j)]; };
-      auto zx = [&](int ii) { return je_ && ((W && (ii == isc - 1 || ii == isc)) || (E && (ii == iec || ii == iec + 1))); };
-      const double cflx = ub > 0 ? ub * dt * m.rdx[o2 - 1] : ub * dt * m.rdx[o2];
-      const double adv_u = advect_along(mord, qu, dxe, zx, ub, cflx, i, ex);
-      auto qv = [&](int jj) { return v[O3(s, i, jj, k)]; };
-      auto dye = [&](int jj) { return m.dy[O2(s, i, jj)]; };
-      auto zy = [&](int jj) { return ie_ && ((S && (jj == jsc - 1 || jj == jsc)) || (N && (jj == jec || jj == jec + 1))); };
-      const double cfly = vb > 0 ? vb * dt * m.rdy[o2 - sj] : vb * dt * m.rdy[o2];
-      const double adv_v = advect_along(mord, qv, dye, zy, vb, cfly, j, ey);
-      kev = 0.5 * dt * (ub * adv_u + vb * adv_v);
+  if (c->nonzero_nord > 3) {
+    fv3::set_error("fv3_d_sw: nord > 3");
+    return -1;
+  }
+  (void)delpc;  // scratch in the reference from here on; nothing downstream reads it
+  if ((rc = dsw_vorticity_launch(ctx, st, u, v, ua, va, uc, vc, ucc, vcc, divgd, ke, vort_a, vort_b, dt, c))) return rc;
+  // K3b: vorticity transport, wind update, vorticity damping and its heat (d_sw.py:1131-1237)
+  {
+    auto mo = [](int hord) { const int a = hord < 0 ? -hord : hord; return a == 10 ? 8 : a; };
+    const int mvt = mo(cfg.hord_vt);
+    double *side_u = fv3::scratch_field(ctx, 4);
+#define DSW_WINDS(M_) dsw_winds_launch<M_>(ctx, st, u, v, ke, vort_a, vort_b, crx, cry, xfx, yfx, delp, heat_s, heat_source, side_u, dt, c)
+    rc = mvt == 8 ? DSW_WINDS(8) : (mvt == 5 ? DSW_WINDS(5) : DSW_WINDS(6));
+#undef DSW_WINDS
+    if (rc) return rc;
+    // the parked first u row of every strip but the first
+    const fv3::StripGeom sg = fv3::strip_geometry(g, fv3::FVTP_PLANES);
+    if (sg.ns > 1) {
+      const int R = sg.rows_per_strip;
+      fv3::launch3d(ctx, st, isc, iec + 1, 0, sg.ns - 1, 0, nz, FV_LAMBDA(int s, int i, int bnd, int k) { FV_DEV_GM
+        const int j = g.halo + (bnd + 1) * R;
+        const int64_t o = O3(s, i, j, k);
+        u[o] = side_u[o];
+      });
     }
-    ke[o] = kev;
-  });
-  // relative vorticity on the A grid, full domain (d_sw.py:301-328)
-  fv3::launch3d(ctx, st, 0, ied + 1, 0, jed + 1, 0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
-    const int64_t o = O3(s, i, j, k), o2 = O2(s, i, j);
-    const double rdy_tmp = m.rarea[o2] * m.dx[o2], rdx_tmp = m.rarea[o2] * m.dy[o2];
-    vort_a[o] = (u[o] - u[o + sj] * m.dx[o2 + sj] / m.dx[o2]) * rdy_tmp + (v[o + 1] * m.dy[o2 + 1] / m.dy[o2] - v[o]) * rdx_tmp;
-  });
-  divergence_damping(ctx, st, u, v, va, vort_b, ua, divgd, vc, uc, delpc, ke, vort_a, dt, c);
-  // absolute vorticity and its transport (d_sw.py:1131-1147)
-  fv3::launch3d(ctx, st, 0, ied + 1, 0, jed + 1, 0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
-    const int64_t o = O3(s, i, j, k);
-    abs_vort[o] = vort_a[o] + m.f0[O2(s, i, j)];
-  });
-  if ((rc = fv3_fvtp2d(ctx, abs_vort, crx, cry, xfx, yfx, fx, fy, nullptr, nullptr, nullptr, cfg.hord_vt, nullptr, nullptr, 0, nz, stream))) return rc;
-  // u_and_v_from_ke (d_sw.py:439-477)
-  fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, 0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
-    const int64_t o = O3(s, i, j, k), o2 = O2(s, i, j);
-    if (i <= iec) u[o] = u[o] * m.dx[o2] + ke[o] - ke[o + 1] + fy[o];
-    if (j <= jec) v[o] = v[o] * m.dy[o2] + ke[o] - ke[o + sj] - fx[o];
-  });
-  // del-n damping fluxes of the relative vorticity (d_sw.py:1160-1166)
-  if ((rc = fv3_delnflux_nosg(ctx, vort_a, ut, vt, c->dn_damp_vt_c, c->nord_v, c->nmax_v, nz, stream))) return rc;
-  // vort_differencing + heat_source_from_vorticity_damping (d_sw.py:349-577) on the compute domain
-  const double d_con_cfg = cfg.d_con;
-  fv3::launch3d(ctx, st, isc, iec + 1, jsc, jec + 1, 0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
-    const bool dc = d_con[k] > DCON_THRESHOLD;
-    auto ubt = [&](int ii, int jj) {  // defined on [isc..iec] x [jsc..jec+1]
-      const int64_t p = O3(s, ii, jj, k);
-      const double vxd = dc ? vort_b[p] - vort_b[p + 1] : 0.0;
-      return (vxd + vt[p]) * m.rdx[O2(s, ii, jj)];
-    };
-    auto vbt = [&](int ii, int jj) {  // defined on [isc..iec+1] x [jsc..jec]
-      const int64_t p = O3(s, ii, jj, k);
-      const double vyd = dc ? vort_b[p] - vort_b[p + sj] : 0.0;
-      return (vyd - ut[p]) * m.rdy[O2(s, ii, jj)];
-    };
-    const int64_t o = O3(s, i, j, k), o2 = O2(s, i, j);
-    double hs = heat_s[o];
-    if (dc) {
-      const double ub0 = ubt(i, j), ub1 = ubt(i, j + 1), vb0 = vbt(i, j), vb1 = vbt(i + 1, j);
-      const double fy0 = u[o] * m.rdx[o2], fy1 = u[o + sj] * m.rdx[o2 + sj];
-      const double fx0 = v[o] * m.rdy[o2], fx1 = v[o + 1] * m.rdy[o2 + 1];
-      const double gy0 = fy0 * ub0, gy1 = fy1 * ub1, gx0 = fx0 * vb0, gx1 = fx1 * vb1;
-      const double u2 = fy0 + fy1, du2 = ub0 + ub1, v2 = fx0 + fx1, dv2 = vb0 + vb1;
-      const double dampterm = m.rsin2[o2] * 0.25 *
-                              ((ub0 * ub0 + ub1 * ub1 + vb0 * vb0 + vb1 * vb1) + 2.0 * (gy0 + gy1 + gx0 + gx1) -
-                               m.cosa_s[o2] * (u2 * dv2 + v2 * du2 + du2 * dv2));
-      hs = delp[o] * (hs - d_con[k] * dampterm);
-    }
-    if (d_con_cfg > DCON_THRESHOLD) heat_source[o] = heat_source[o] + hs;
-  });
-  // update_u_and_v (d_sw.py:582-608)
-  fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, 0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
-    if (!(damp_vt[k] > 1e-5)) return;
-    const int64_t o = O3(s, i, j, k);
-    if (i <= iec) u[o] = u[o] + vt[o];
-    if (j <= jec) v[o] = v[o] - ut[o];
-  });
+  }
   return fv3::check_launch("fv3_d_sw");
 }
 

@@ -216,34 +216,6 @@ __global__ void __launch_bounds__(PLANE_THREADS, 2) kplane(F f, int k0, int rows
   }
   f((int)blockIdx.y, k0 + (int)blockIdx.x, b);
 }
-// experiment: one CTA per SM, the whole register file for 512 threads (FV3_ONE_CTA=1, with FV3_FORCE_STRIPS=1)
-template <class F>
-__global__ void __launch_bounds__(PLANE_THREADS, 1) kplane1(F f, int k0, int rows_per_strip, int res_rows, int ahead) {
-  extern __shared__ __align__(128) double plane_smem[];
-  __shared__ unsigned long long plane_bar;
-  Block b = make_block(c_g, plane_smem, (int)blockIdx.z, rows_per_strip, res_rows);
-  b.bar = &plane_bar;
-  if (threadIdx.x == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&plane_bar)) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  {  // blocks are dispatched level-fastest, then subdomain, then strip: `ahead` subdomains later = one wave later
-    int sn = (int)blockIdx.y + ahead, zn = (int)blockIdx.z;
-    if (sn >= (int)gridDim.y) {
-      sn -= (int)gridDim.y;
-      ++zn;
-    }
-    if (zn < (int)gridDim.z && sn < (int)gridDim.y) {
-      int ja, jb, r0, r1;
-      strip_rows(c_g, zn, rows_per_strip, ja, jb, r0, r1);
-      b.s_next = sn;
-      b.r0_next = r0;
-      b.nrows_next = r1 - r0;
-    }
-  }
-  f((int)blockIdx.y, k0 + (int)blockIdx.x, b);
-}
 #endif
 
 template <class F>
@@ -295,16 +267,6 @@ inline int launch_planes(const fv3_ctx *ctx, cudaStream_t st, int k0, int k1, in
     resident = 2 * sms;
   }
   const int ahead = (resident + (k1 - k0) - 1) / (k1 - k0);
-  static int one_cta = -1;
-  if (one_cta < 0) one_cta = getenv("FV3_ONE_CTA") ? 1 : 0;
-  if (one_cta) {
-    static size_t configured1 = 0;
-    if (bytes > configured1) {
-      cudaFuncSetAttribute(kplane1<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-      configured1 = bytes;
-    }
-    kplane1<<<dim3(k1 - k0, ctx->g.n_sub, sg.ns), PLANE_THREADS, bytes, st>>>(f, k0, sg.rows_per_strip, sg.res_rows, ahead);
-  } else
   kplane<<<dim3(k1 - k0, ctx->g.n_sub, sg.ns), PLANE_THREADS, bytes, st>>>(f, k0, sg.rows_per_strip, sg.res_rows, ahead);
   ++g_launches;
   return 0;

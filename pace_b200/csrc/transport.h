@@ -22,6 +22,7 @@ namespace fv3 {
 constexpr int FVTP_PLANES = 5;
 struct PlaneArgs {
   const double *q, *crx, *cry, *xfx, *yfx, *xu, *yu;
+  const double *add2d = nullptr;  // optional 2-D field (this subdomain's plane) added to q as it is loaded
 };
 
 // NC: the final-flux operands xu / yu are read-only for the whole kernel (read through the non-coherent path); false
@@ -53,13 +54,14 @@ FV_DEV void fvtp2d_plane(const fv3_geom &g, const fv3_grid &m, int s, int k, con
   b.bulk_begin(1, sj);
   b.bulk_rows(Q, q, sj);
   b.bulk_wait();
+  if (a.add2d) b.rect(0, nwi, rl, rh, [&](int i, int j) { Q[j * sj + i] = Q[j * sj + i] + a.add2d[j * sj + i]; });
   b.par(4 * h * h, [&](int t) {
     const int c = t / (h * h), r = t - c * h * h, a1 = r / h, b1 = r - a1 * h;
     const int i = (c & 1) ? iec + 1 + a1 : a1, j = (c & 2) ? jec + 1 + b1 : b1;
     if (j < rl || j >= rh) return;
     int ii = i, jj = j;
     corner_y(g, s, ii, jj);
-    if (ii != i || jj != j) Q[j * sj + i] = q[jj * sj + ii];
+    if (ii != i || jj != j) Q[j * sj + i] = a.add2d ? q[jj * sj + ii] + a.add2d[jj * sj + ii] : q[jj * sj + ii];
   });
   // 2. inner y sweep on q: all columns, faces ja .. jb
   ppm_sweep<MORD, false>(b, Q, sj, cry, dya, ey, 0, nwi, ja, jb, [&](int p, double val) { A[p] = val; });
@@ -70,7 +72,7 @@ FV_DEV void fvtp2d_plane(const fv3_geom &g, const fv3_grid &m, int s, int k, con
     if (j < rl || j >= rh) return;
     int ii = i, jj = j;
     corner_x(g, s, ii, jj);
-    Q[j * sj + i] = q[jj * sj + ii];
+    Q[j * sj + i] = a.add2d ? q[jj * sj + ii] + a.add2d[jj * sj + ii] : q[jj * sj + ii];
   });
   // 4. inner x sweep on q: resident rows, faces isc .. iec+1
   ppm_sweep<MORD, true>(b, Q, sj, crx, dxa, ex, rl, rh - rl, isc, iec + 1, [&](int p, double val) { B[p] = val; });
