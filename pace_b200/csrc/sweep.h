@@ -90,23 +90,37 @@ inline
 // passes its own face rows).
 // fin(p, value): what to do with the value at plane offset p; it must not write Qs.
 template <int MORD, bool XDIR, class Fin>
-FV_DEV void ppm_sweep(const Block &b, const double *Qs, int sj, const double *cg, const double *dxg, const Edge1D &e,
-                      int l0, int nl, int f0, int f1, Fin fin) {
-  constexpr int R = SWEEP_R;
-  const int st = XDIR ? 1 : sj, ls = XDIR ? sj : 1;
-  if (nl <= 0 || f1 < f0) return;  // uniform over the block
-  // faces the edge tasks own (skipped by the bulk tasks); empty ranges away from tile edges
-  const int elo0 = e.start, elo1 = e.lo ? e.start + 2 : e.start - 1;  // [elo0, elo1]
-  const int ehi0 = e.hi ? e.end - 1 : e.end + 2, ehi1 = e.end + 1;    // [ehi0, ehi1]
-  // faces the bulk tasks store: [f0, f1] minus the edge faces (contiguous with the ends of the line)
-  const int fv0 = (e.lo && f0 <= elo1) ? elo1 + 1 : f0, fv1 = (e.hi && f1 >= ehi0) ? ehi0 - 1 : f1;
-  const unsigned nfv = fv1 >= fv0 ? (unsigned)(fv1 - fv0) : 0u;
-  // x sweeps: groups start at multiples of R so that the 128-bit window loads are aligned
-  const int fb = XDIR ? (fv0 & ~(R - 1)) : fv0;
-  const int ng = fv1 >= fv0 ? (fv1 - fb) / R + 1 : 0;
-  const int nbulk = fv1 >= fv0 ? ng * nl : 0, nedge = (e.lo || e.hi) ? 2 * nl : 0;
-  const float inv = 1.0f / (float)(XDIR ? ng : nl);
-  b.par(nbulk + nedge, [&](int t) {
+struct Sweep {
+  const double *Qs, *cg, *dxg;
+  Edge1D e;
+  int sj, l0, nl, f0, f1, fv0, fb, ng, nbulk, n;  // n: tasks of this sweep (bulk + tile-edge)
+  unsigned nfv;
+  float inv;
+  Fin fin;
+
+  FV_DEV Sweep(const double *Qs_, int sj_, const double *cg_, const double *dxg_, const Edge1D &e_, int l0_, int nl_, int f0_,
+               int f1_, Fin fin_)
+      : Qs(Qs_), cg(cg_), dxg(dxg_), e(e_), sj(sj_), l0(l0_), nl(nl_), f0(f0_), f1(f1_), fin(fin_) {
+    constexpr int R = SWEEP_R;
+    // faces the edge tasks own (skipped by the bulk tasks); empty ranges away from tile edges
+    const int elo1 = e.lo ? e.start + 2 : e.start - 1;  // [e.start, elo1]
+    const int ehi0 = e.hi ? e.end - 1 : e.end + 2;      // [ehi0, e.end + 1]
+    // faces the bulk tasks store: [f0, f1] minus the edge faces (contiguous with the ends of the line)
+    fv0 = (e.lo && f0 <= elo1) ? elo1 + 1 : f0;
+    const int fv1 = (e.hi && f1 >= ehi0) ? ehi0 - 1 : f1;
+    const bool any = nl > 0 && f1 >= f0;
+    nfv = fv1 >= fv0 ? (unsigned)(fv1 - fv0) : 0u;
+    // x sweeps: groups start at multiples of R so that the 128-bit window loads are aligned
+    fb = XDIR ? (fv0 & ~(R - 1)) : fv0;
+    ng = (any && fv1 >= fv0) ? (fv1 - fb) / R + 1 : 0;
+    nbulk = ng * nl;
+    n = any ? nbulk + ((e.lo || e.hi) ? 2 * nl : 0) : 0;
+    inv = 1.0f / (float)(XDIR ? (ng > 0 ? ng : 1) : (nl > 0 ? nl : 1));
+  }
+
+  FV_DEV void run(int t) const {
+    constexpr int R = SWEEP_R;
+    const int st = XDIR ? 1 : sj, ls = XDIR ? sj : 1;
     if (t < nbulk) {
       // task -> (line, group): groups fastest for x sweeps (a warp reads whole row segments), lines fastest for y
       // sweeps (consecutive lanes own consecutive columns)
@@ -197,6 +211,31 @@ FV_DEV void ppm_sweep(const Block &b, const double *Qs, int sj, const double *cg
         fin(p, ppm_edge_face<MORD>(Qs + l * ls, dxg + l * ls, st, cg[p], f, e));
       }
     }
+  }
+};
+
+template <int MORD, bool XDIR, class Fin>
+FV_DEV Sweep<MORD, XDIR, Fin> make_sweep(const double *Qs, int sj, const double *cg, const double *dxg, const Edge1D &e, int l0,
+                                        int nl, int f0, int f1, Fin fin) {
+  return Sweep<MORD, XDIR, Fin>(Qs, sj, cg, dxg, e, l0, nl, f0, f1, fin);
+}
+
+// one sweep = one block-wide pass
+template <int MORD, bool XDIR, class Fin>
+FV_DEV void ppm_sweep(const Block &b, const double *Qs, int sj, const double *cg, const double *dxg, const Edge1D &e,
+                      int l0, int nl, int f0, int f1, Fin fin) {
+  const auto sw = make_sweep<MORD, XDIR>(Qs, sj, cg, dxg, e, l0, nl, f0, f1, fin);
+  b.par(sw.n, [&](int t) { sw.run(t); });
+}
+// two independent sweeps (neither reads what the other writes) in ONE block-wide pass: one barrier instead of two and
+// twice the tasks to hide latencies behind
+template <class S1, class S2>
+FV_DEV void ppm_sweep_pair(const Block &b, const S1 &s1, const S2 &s2) {
+  b.par(s1.n + s2.n, [&](int t) {
+    if (t < s1.n)
+      s1.run(t);
+    else
+      s2.run(t - s1.n);
   });
 }
 

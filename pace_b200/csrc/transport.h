@@ -55,27 +55,37 @@ FV_DEV void fvtp2d_plane(const fv3_geom &g, const fv3_grid &m, int s, int k, con
   b.bulk_rows(Q, q, sj);
   b.bulk_wait();
   if (a.add2d) b.rect(0, nwi, rl, rh, [&](int i, int j) { Q[j * sj + i] = Q[j * sj + i] + a.add2d[j * sj + i]; });
-  b.par(4 * h * h, [&](int t) {
-    const int c = t / (h * h), r = t - c * h * h, a1 = r / h, b1 = r - a1 * h;
-    const int i = (c & 1) ? iec + 1 + a1 : a1, j = (c & 2) ? jec + 1 + b1 : b1;
-    if (j < rl || j >= rh) return;
-    int ii = i, jj = j;
-    corner_y(g, s, ii, jj);
-    if (ii != i || jj != j) Q[j * sj + i] = a.add2d ? q[jj * sj + ii] + a.add2d[jj * sj + ii] : q[jj * sj + ii];
-  });
-  // 2. inner y sweep on q: all columns, faces ja .. jb
-  ppm_sweep<MORD, false>(b, Q, sj, cry, dya, ey, 0, nwi, ja, jb, [&](int p, double val) { A[p] = val; });
-  // 3. cube-corner blocks as copy_corners_x leaves them
-  b.par(4 * h * h, [&](int t) {
-    const int c = t / (h * h), r = t - c * h * h, a1 = r / h, b1 = r - a1 * h;
-    const int i = (c & 1) ? iec + 1 + a1 : a1, j = (c & 2) ? jec + 1 + b1 : b1;
-    if (j < rl || j >= rh) return;
-    int ii = i, jj = j;
-    corner_x(g, s, ii, jj);
-    Q[j * sj + i] = a.add2d ? q[jj * sj + ii] + a.add2d[jj * sj + ii] : q[jj * sj + ii];
-  });
-  // 4. inner x sweep on q: resident rows, faces isc .. iec+1
-  ppm_sweep<MORD, true>(b, Q, sj, crx, dxa, ex, rl, rh - rl, isc, iec + 1, [&](int p, double val) { B[p] = val; });
+  // the cube-corner halo blocks need their copy_corners_y / copy_corners_x forms only on tile-corner subdomains, and
+  // only in the strips that hold rows of the y halo (block-uniform)
+  const bool fix = (ex.lo || ex.hi) && (ey.lo || ey.hi) && (rl < jsc || rh > jec + 1);
+  auto inner_y = make_sweep<MORD, false>(Q, sj, cry, dya, ey, 0, nwi, ja, jb, [&](int p, double val) { A[p] = val; });
+  auto inner_x = make_sweep<MORD, true>(Q, sj, crx, dxa, ex, rl, rh - rl, isc, iec + 1, [&](int p, double val) { B[p] = val; });
+  if (fix) {
+    b.par(4 * h * h, [&](int t) {
+      const int c = t / (h * h), r = t - c * h * h, a1 = r / h, b1 = r - a1 * h;
+      const int i = (c & 1) ? iec + 1 + a1 : a1, j = (c & 2) ? jec + 1 + b1 : b1;
+      if (j < rl || j >= rh) return;
+      int ii = i, jj = j;
+      corner_y(g, s, ii, jj);
+      if (ii != i || jj != j) Q[j * sj + i] = a.add2d ? q[jj * sj + ii] + a.add2d[jj * sj + ii] : q[jj * sj + ii];
+    });
+    // 2. inner y sweep on q: all columns, faces ja .. jb
+    b.par(inner_y.n, [&](int t) { inner_y.run(t); });
+    // 3. cube-corner blocks as copy_corners_x leaves them
+    b.par(4 * h * h, [&](int t) {
+      const int c = t / (h * h), r = t - c * h * h, a1 = r / h, b1 = r - a1 * h;
+      const int i = (c & 1) ? iec + 1 + a1 : a1, j = (c & 2) ? jec + 1 + b1 : b1;
+      if (j < rl || j >= rh) return;
+      int ii = i, jj = j;
+      corner_x(g, s, ii, jj);
+      Q[j * sj + i] = a.add2d ? q[jj * sj + ii] + a.add2d[jj * sj + ii] : q[jj * sj + ii];
+    });
+    // 4. inner x sweep on q: resident rows, faces isc .. iec+1
+    b.par(inner_x.n, [&](int t) { inner_x.run(t); });
+  } else {
+    // 2 + 4. no corner block in reach: both inner sweeps read the same plane, one pass
+    ppm_sweep_pair(b, inner_y, inner_x);
+  }
   // 5. transverse updates: q_i (into Q, owned rows) and q_j (into D, compute columns of the resident rows)
   b.rect(0, nwi, rl, rh, [&](int i, int j) {
     const int p = j * sj + i;
@@ -91,13 +101,14 @@ FV_DEV void fvtp2d_plane(const fv3_geom &g, const fv3_grid &m, int s, int k, con
       D[p] = (qv * ar + f0 - f1) / (ar + x0 - x1);
     }
   });
-  // 6. outer x sweep on q_i (owned rows) -> x flux, in place over fx_in
+  // 6 + 7. outer x sweep on q_i (owned rows) -> x flux in place over fx_in; outer y sweep on q_j (compute columns) -> y
+  // flux in place over fy_in: independent, one pass
   const double *xu = a.xu + ob, *yu = a.yu + ob;
-  ppm_sweep<MORD, true>(b, Q, sj, crx, dxa, ex, ja, jb - ja, isc, iec + 1,
-                             [&](int p, double val) { B[p] = 0.5 * (val + B[p]) * (NC ? FV_LDG(xu + p) : xu[p]); });
-  // 7. outer y sweep on q_j (compute columns) -> y flux, in place over fy_in
-  ppm_sweep<MORD, false>(b, D, sj, cry, dya, ey, isc, nx, ja, jb,
-                              [&](int p, double val) { A[p] = 0.5 * (val + A[p]) * (NC ? FV_LDG(yu + p) : yu[p]); });
+  auto outer_x = make_sweep<MORD, true>(Q, sj, crx, dxa, ex, ja, jb - ja, isc, iec + 1,
+                                        [&](int p, double val) { B[p] = 0.5 * (val + B[p]) * (NC ? FV_LDG(xu + p) : xu[p]); });
+  auto outer_y = make_sweep<MORD, false>(D, sj, cry, dya, ey, isc, nx, ja, jb,
+                                         [&](int p, double val) { A[p] = 0.5 * (val + A[p]) * (NC ? FV_LDG(yu + p) : yu[p]); });
+  ppm_sweep_pair(b, outer_x, outer_y);
 }
 
 #ifndef FV3_HOSTSIM
