@@ -17,7 +17,7 @@ CUDA_LIB = os.path.join(HERE, "libfv3b200.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--extended-lambda",
-    "-fmad=false",  # fp64 parity with the numpy backend: no FMA contraction (DESIGN.md "parity budget")
+    "-fmad=" + os.environ.get("FV3_FMAD", "false"),  # fp64 parity with the numpy backend: no FMA contraction (DESIGN.md "parity budget")
     "-Xcompiler", "-fPIC",
 ]
 

@@ -19,7 +19,10 @@ kernel difference was checked two ways in the build container: (1) this repo's k
 grid and initial state match every field of all 6 ranks at the c12 tolerances (tests/test_dycore_step.py with
 PACE_B200_STEP_CASE=c48 on the full dump of oracle/refshim/gen_golden.py, too large to commit; run below whenever that
 dump is present); (2) this repo's kernels run from the two initial states differ from each other at exactly those
-columns by exactly those amounts.
+columns by exactly those amounts.  The strict (no-allowance) comparisons from the reference's own inputs that ARE
+committed and run on the GPU are tests/test_step_strict.py: c12, c12k2n6, c24L2, c24L2k2n3, c12sat, c12satk2 (a C48
+input set would be 40 MB); what this file adds is BASELINE configs[1]'s size (48 x 48 subdomains, automatic strip
+decomposition) and the generator end to end.
 """
 import json
 import os

@@ -1,8 +1,9 @@
 """Full DynamicalCore.step_dynamics on the c12 baroclinic case, all 6 subdomains in ONE process (batched), compared
 with the final state of the unmodified reference (numpy backend).
 
-Needs the full 6-rank reference dump (oracle/refshim/gen_golden.py); it is too large to commit, so this test runs in
-the build container only (the per-stage tests and tests/test_dycore_golden.py cover the GPU box).
+Runs from the committed subset tests/golden/c12_step (grid + initial state of all 6 ranks, final state of ranks 0 and
+3) or, when present, from a full 6-rank dump of oracle/refshim/gen_golden.py (PACE_B200_STEP_CASE selects the case).
+The strict multi-substep / layout (2,2) / do_sat_adj cases are in tests/test_step_strict.py.
 """
 import os
 from datetime import timedelta

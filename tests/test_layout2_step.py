@@ -9,8 +9,10 @@ by oracle/refshim/gen_golden.py, reduced by tests/golden/make_layout2_step.py) h
 and after the step on a subsample of levels.  Tolerances and the bounded wind-outlier allowance are those of
 tests/test_c48_step.py (same reason: the initial winds agree to 1e-12 m/s, not bit for bit); the cell-centred winds ua,
 va are 4-point interpolations of u, v, so one flipped column touches more of a 12 x 12 subdomain: 8 % of the points,
-each still within 1e-2 m/s.  The strict form — reference grid and initial state in, every field of all 24 ranks at
-the c12 tolerances — runs whenever the full dump is present ($PACE_B200_GOLDEN_CACHE/c24L2; build container) and passes.
+each still within 1e-2 m/s.  The STRICT form of this case — the reference's own grid and initial state in (committed:
+tests/golden/c24L2_inputs, all 24 ranks), every prognostic field compared with no outlier allowance, on the GPU — is
+tests/test_step_strict.py[c24L2] (k_split = n_split = 1) and [c24L2k2n3] (multi-substep, 8 non-zero tracers); this file
+keeps what those cannot check: that this repo's OWN grid generator and analytic initial state reproduce the reference's.
 """
 import json
 import os
