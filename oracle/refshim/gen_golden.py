@@ -31,6 +31,7 @@ def main():
                     help="BASELINE configs[3]: tracer m (1..7) = qvapor * (m + 1) / 10 before the first step (SURVEY.md §8d)")
     ap.add_argument("--stages", nargs="*", default=None, help="capture only these stages (default: all)")
     ap.add_argument("--do-sat-adj", action="store_true", help="the stock baroclinic_c12.yaml setting (row f1)")
+    ap.add_argument("--hord", type=int, default=None, help="override hord_dp = hord_tm = hord_vt = hord_mt (5: the other monotonic switch)")
     args = ap.parse_args()
 
     from oracle.refshim import runner
@@ -40,6 +41,8 @@ def main():
     overrides = dict(n_split=args.n_split, k_split=args.k_split)
     if args.do_sat_adj:
         overrides["do_sat_adj"] = True
+    if args.hord is not None:
+        overrides.update(hord_dp=args.hord, hord_tm=args.hord, hord_vt=args.hord, hord_mt=args.hord)
     ctxs, cap = runner.run(
         args.nx, (args.layout, args.layout), nsteps=args.nsteps, capture_ranks=tuple(args.capture_ranks),
         config_overrides=overrides, capture_step=args.capture_step, stages=args.stages,
@@ -58,7 +61,7 @@ def main():
             flat.update({f"out.{k}": v for k, v in rec["out"].items()})
             np.savez(os.path.join(d, key + ".npz"), **flat)
     meta = dict(capture_step=args.capture_step, nx=args.nx, layout=args.layout, nsteps=args.nsteps, n_split=args.n_split, k_split=args.k_split,
-                fill_tracers=bool(args.fill_tracers), do_sat_adj=bool(args.do_sat_adj), timing=ctxs[0].get("timing"), wall=time.time() - t0, config=runner.C12_CONFIG,
+                fill_tracers=bool(args.fill_tracers), do_sat_adj=bool(args.do_sat_adj), hord=args.hord, timing=ctxs[0].get("timing"), wall=time.time() - t0, config=runner.C12_CONFIG,
                 reference="ai2cm/pace @ /root/reference, numpy backend via oracle/refshim")
     with open(os.path.join(args.out, "meta.json"), "w") as f:
         json.dump(meta, f, indent=1, default=str)

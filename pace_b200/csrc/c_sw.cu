@@ -2,7 +2,7 @@
 //   fv3_c_sw  <-  CGridShallowWaterDynamics.__call__ (fv3core/pace/fv3core/stencils/c_sw.py:607-766) including
 //                 DGrid2AGrid2CGridVectors.__call__ (d2a2c_vect.py:547-655) and the corner fills it uses
 //                 (stencils/pace/stencils/corners.py:130-304).
-// The reference's 24 stencil launches are regrouped into 11 launches; region-restricted statements become
+// The reference's 24 stencil launches are regrouped into 8 launches; region-restricted statements become
 // per-subdomain tile-edge predicates (geom.edge).  Values, not statement order, are reproduced: every point is
 // computed with the formula that "wins" in the reference's statement sequence.
 #include "common.h"
@@ -18,23 +18,35 @@ constexpr double BIG = 1e30;
 
 FV_HD double contravariant(double v1, double v2, double cosa, double rsin2) { return (v1 - v2 * cosa) * rsin2; }
 
-// fill_corners_2cells_x (dir 0) / _y (dir 1) of three fields in place (corners.py:130-166,235-270)
-void corner_fill_2cells(const fv3_ctx *ctx, cudaStream_t st, double *delp, double *pt, double *w, int dir) {
-  const fv3_geom g = ctx->g;
-  const int h = g.halo, isc = h, iec = h + g.nx - 1, jsc = h, jec = h + g.ny - 1;
-  fv3::launch3d(ctx, st, 0, 8, 0, 3, 0, g.nz, FV_LAMBDA(int s, int id, int f, int k) { FV_DEV_GM
-    const int corner = id / 2, d = id % 2 + 1;
-    const bool west = (corner == 0 || corner == 2), south = (corner < 2);
-    if (!((west ? fv3::on_west(g, s) : fv3::on_east(g, s)) && (south ? fv3::on_south(g, s) : fv3::on_north(g, s))))
-      return;
-    double *q = f == 0 ? delp : (f == 1 ? pt : w);
-    const int ic = west ? isc - 1 : iec + 1, jc = south ? jsc - 1 : jec + 1;
-    const int xs = west ? -1 : 1, ys = south ? -1 : 1;
-    if (dir == 0)
-      q[O3(s, ic + xs * (d - 1), jc, k)] = q[O3(s, ic, jc - ys * d, k)];
-    else
-      q[O3(s, ic, jc + ys * (d - 1), k)] = q[O3(s, ic - xs * d, jc, k)];
-  });
+// fill_corners_2cells_x / _y (corners.py:130-166,235-270) as read-time remaps: the cell (i, j) of a cube-corner halo block
+// reads the cell the in-place fill would have copied into it
+FV_HD void fill2_x(const fv3_geom &g, int s, int &i, int &j) {
+  const int isc = g.halo, iec = g.halo + g.nx - 1, jsc = g.halo, jec = g.halo + g.ny - 1;
+  const bool south = j == jsc - 1, north = j == jec + 1;
+  if (!(south || north)) return;
+  if (!(south ? fv3::on_south(g, s) : fv3::on_north(g, s))) return;
+  const int ys = south ? -1 : 1;
+  if (fv3::on_west(g, s) && (i == isc - 1 || i == isc - 2)) {
+    j = j - ys * (isc - i);
+    i = isc - 1;
+  } else if (fv3::on_east(g, s) && (i == iec + 1 || i == iec + 2)) {
+    j = j - ys * (i - iec);
+    i = iec + 1;
+  }
+}
+FV_HD void fill2_y(const fv3_geom &g, int s, int &i, int &j) {
+  const int isc = g.halo, iec = g.halo + g.nx - 1, jsc = g.halo, jec = g.halo + g.ny - 1;
+  const bool west = i == isc - 1, east = i == iec + 1;
+  if (!(west || east)) return;
+  if (!(west ? fv3::on_west(g, s) : fv3::on_east(g, s))) return;
+  const int xs = west ? -1 : 1;
+  if (fv3::on_south(g, s) && (j == jsc - 1 || j == jsc - 2)) {
+    i = i - xs * (jsc - j);
+    j = jsc - 1;
+  } else if (fv3::on_north(g, s) && (j == jec + 1 || j == jec + 2)) {
+    i = i - xs * (j - jec);
+    j = jec + 1;
+  }
 }
 
 }  // namespace
@@ -52,7 +64,6 @@ int fv3_c_sw(fv3_ctx *ctx, double *delp, double *pt, const double *u, const doub
   const int ied = iec + h, jed = jec + h;
   const int sj = g.sj;
   double *utmp = fv3::scratch_field(ctx, 0), *vtmp = fv3::scratch_field(ctx, 1);
-  double *fx = fv3::scratch_field(ctx, 2), *fx1 = fv3::scratch_field(ctx, 3), *fx2 = fv3::scratch_field(ctx, 4);
   double *ke = fv3::scratch_field(ctx, 5), *vort = fv3::scratch_field(ctx, 6);
   int npt = 4;
   if (npt > g.nx - 1 || npt > g.ny - 1) npt = 0;
@@ -196,46 +207,60 @@ int fv3_c_sw(fv3_ctx *ctx, double *delp, double *pt, const double *u, const doub
     });
   }
 
-  // Kc1: fill_corners_2cells_x on delp, pt, w, in place (c_sw.py:693, corners.py:130-166)
-  corner_fill_2cells(ctx, st, delp, pt, w, 0);
-
-  // K5: first-order upwind x-fluxes (c_sw.py:229-258)
-  fv3::launch3d(ctx, st, isc - 1, iec + 3, jsc - 1, jec + 2, 0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
-    const int64_t o = O3(s, i, j, k);
-    const double utc = ut[o];
-    const int64_t ou = utc > 0.0 ? o - 1 : o;
-    const double f1 = utc * delp[ou];
-    fx1[o] = f1;
-    fx[o] = f1 * pt[ou];
-    fx2[o] = f1 * w[ou];
-  });
-
-  corner_fill_2cells(ctx, st, delp, pt, w, 1);
-
-  // K6: transport of delp, pt, w; upstream kinetic energy and vorticity (c_sw.py:261-364)
+  // K5 + K6: first-order upwind transport of delp, pt, w (c_sw.py:229-345), upstream kinetic energy and vorticity
+  // (:347-364).  The x fluxes of a cell's two faces are formed on the fly (two multiplies each) instead of going through
+  // three scratch fields; the in-place 2-cell corner fills of delp, pt, w (corners.py:130-166,235-270) are read-time
+  // index remaps — the x fluxes see the cells as fill_corners_2cells_x leaves them, everything else as
+  // fill_corners_2cells_y does — and the cells the reference leaves modified are written by a small launch afterwards.
   fv3::launch3d(ctx, st, isc - 1, iec + 2, jsc - 1, jec + 2, 0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     const bool W = fv3::on_west(g, s), E = fv3::on_east(g, s), S = fv3::on_south(g, s), N = fv3::on_north(g, s);
     const int64_t o = O3(s, i, j, k), o2 = O2(s, i, j);
+    const bool near_corner = (W || E) && (S || N) && (i <= isc || i >= iec) && (j <= jsc || j >= jec);
+    auto rd = [&](const double *q, int ii, int jj, bool xfill) {
+      if (near_corner) {
+        if (xfill)
+          fill2_x(g, s, ii, jj);
+        else
+          fill2_y(g, s, ii, jj);
+      }
+      return q[O3(s, ii, jj, k)];
+    };
+    double fx1a, fxa, fx2a, fx1b, fxb, fx2b;
+    {
+      const double utc = ut[o];
+      const int iu = utc > 0.0 ? i - 1 : i;
+      fx1a = utc * rd(delp, iu, j, true);
+      fxa = fx1a * rd(pt, iu, j, true);
+      fx2a = fx1a * rd(w, iu, j, true);
+    }
+    {
+      const double utc = ut[o + 1];
+      const int iu = utc > 0.0 ? i : i + 1;
+      fx1b = utc * rd(delp, iu, j, true);
+      fxb = fx1b * rd(pt, iu, j, true);
+      fx2b = fx1b * rd(w, iu, j, true);
+    }
     double fy1a, fya, fy2a, fy1b, fyb, fy2b;
     {
       const double vtc = vt[o];
-      const int64_t ou = vtc > 0.0 ? o - sj : o;
-      fy1a = vtc * delp[ou];
-      fya = fy1a * pt[ou];
-      fy2a = fy1a * w[ou];
+      const int ju = vtc > 0.0 ? j - 1 : j;
+      fy1a = vtc * rd(delp, i, ju, false);
+      fya = fy1a * rd(pt, i, ju, false);
+      fy2a = fy1a * rd(w, i, ju, false);
     }
     {
       const double vtc = vt[o + sj];
-      const int64_t ou = vtc > 0.0 ? o : o + sj;
-      fy1b = vtc * delp[ou];
-      fyb = fy1b * pt[ou];
-      fy2b = fy1b * w[ou];
+      const int ju = vtc > 0.0 ? j : j + 1;
+      fy1b = vtc * rd(delp, i, ju, false);
+      fyb = fy1b * rd(pt, i, ju, false);
+      fy2b = fy1b * rd(w, i, ju, false);
     }
     const double ra = m.rarea[o2];
-    const double dpc = delp[o] + (fx1[o] - fx1[o + 1] + fy1a - fy1b) * ra;
+    const double dp0 = rd(delp, i, j, false), pt0 = rd(pt, i, j, false), w0 = rd(w, i, j, false);
+    const double dpc = dp0 + (fx1a - fx1b + fy1a - fy1b) * ra;
     delpc[o] = dpc;
-    ptc[o] = (pt[o] * delp[o] + (fx[o] - fx[o + 1] + fya - fyb) * ra) / dpc;
-    omga[o] = (w[o] * delp[o] + (fx2[o] - fx2[o + 1] + fy2a - fy2b) * ra) / dpc;
+    ptc[o] = (pt0 * dp0 + (fxa - fxb + fya - fyb) * ra) / dpc;
+    omga[o] = (w0 * dp0 + (fx2a - fx2b + fy2a - fy2b) * ra) / dpc;
     const double uav = ua[o], vav = va[o];
     double kev = uav > 0.0 ? uc[o] : uc[o + 1];
     double vo = vav > 0.0 ? vc[o] : vc[o + sj];
@@ -244,6 +269,23 @@ int fv3_c_sw(fv3_ctx *ctx, double *delp, double *pt, const double *u, const doub
     if ((E && i == iec) || (W && i == isc - 1)) kev = uav <= 0.0 ? kev * m.sin_sg3[o2] + v[o + 1] * m.cos_sg3[o2] : kev;
     if ((E && i == iec + 1) || (W && i == isc)) kev = uav > 0.0 ? kev * m.sin_sg1[o2] + v[o] * m.cos_sg1[o2] : kev;
     ke[o] = 0.5 * dt2 * (uav * kev + vav * vo);
+  });
+  // what the in-place corner fills leave behind: per tile corner (ic, jc) and (ic, jc + ys) hold their y fill,
+  // (ic + xs, jc) its x fill (the sources are cells no fill touches)
+  fv3::launch3d(ctx, st, 0, 12, 0, 3, 0, nz, FV_LAMBDA(int s, int id, int f, int k) { FV_DEV_GM
+    const int corner = id / 3, c = id % 3;
+    const bool west = (corner == 0 || corner == 2), south = (corner < 2);
+    if (!((west ? fv3::on_west(g, s) : fv3::on_east(g, s)) && (south ? fv3::on_south(g, s) : fv3::on_north(g, s))))
+      return;
+    double *q = f == 0 ? delp : (f == 1 ? pt : w);
+    const int ic = west ? isc - 1 : iec + 1, jc = south ? jsc - 1 : jec + 1;
+    const int xs = west ? -1 : 1, ys = south ? -1 : 1;
+    if (c == 0)
+      q[O3(s, ic, jc, k)] = q[O3(s, ic - xs, jc, k)];
+    else if (c == 1)
+      q[O3(s, ic, jc + ys, k)] = q[O3(s, ic - 2 * xs, jc, k)];
+    else
+      q[O3(s, ic + xs, jc, k)] = q[O3(s, ic, jc - 2 * ys, k)];
   });
 
   // K7: absolute vorticity at cell corners (c_sw.py:367-408)

@@ -101,7 +101,7 @@ def c12_sat():
     from make_committed import reduce_stage
 
     inp = os.path.join(HERE, "c12_step")
-    for case in ("c12sat", "c12satk2"):
+    for case in ("c12sat", "c12satk2", "c12hord5"):
         src, dst = os.path.join(CACHE, case), os.path.join(HERE, case + "_step")
         if not os.path.exists(os.path.join(src, "meta.json")):
             continue

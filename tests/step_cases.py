@@ -33,6 +33,8 @@ CASES = {
     # do_sat_adj = True: the stock baroclinic_c12.yaml, and k_split = 2 with 8 non-zero tracers
     "c12sat": dict(dir="c12sat_step", substeps=1),
     "c12satk2": dict(dir="c12satk2_step", substeps=2),
+    # hord_dp = hord_tm = hord_vt = hord_mt = 5 (the other monotonicity switch of xppm.py:47-61 / xtp_u.py), n_split = 2
+    "c12hord5": dict(dir="c12hord5_step", substeps=2),
 }
 
 
@@ -83,8 +85,11 @@ def build(meta, grids, s0, dev=None, process_comm=None):
         s0 = [s0[r] for r in comm.local_ranks]
     gd = GridData.from_arrays(qf, grids)
     damp = DampingCoefficients.from_arrays(qf, grids)
+    extra = {}
+    if meta.get("hord") is not None:
+        extra = dict(hord_dp=meta["hord"], hord_tm=meta["hord"], hord_vt=meta["hord"], hord_mt=meta["hord"])
     cfg = baroclinic_config(nx, (layout, layout), n_split=meta.get("n_split", 1), k_split=meta.get("k_split", 1),
-                            do_sat_adj=bool(meta.get("do_sat_adj", False)))
+                            do_sat_adj=bool(meta.get("do_sat_adj", False)), **extra)
     rt = Runtime(comm, qf, gd, damp, cfg)
     sf = StencilFactory(None, GridIndexing.from_sizer_and_communicator(qf.sizer, comm), rt)
     state = DycoreState.init_from_numpy_arrays(s0, qf)
