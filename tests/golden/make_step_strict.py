@@ -120,7 +120,7 @@ def c12_sat():
             np.savez_compressed(os.path.join(dst, f"state1_rank{r}.npz"), **{n: z[n] for n in FIELDS + ["qcld"]})
         sd = os.path.join(dst, "stage_rank0")
         os.makedirs(sd, exist_ok=True)
-        for f in sorted(os.listdir(os.path.join(src, "stage_rank0"))):
+        for f in sorted(os.listdir(os.path.join(src, "stage_rank0"))) if os.path.isdir(os.path.join(src, "stage_rank0")) else []:
             if f.startswith("SatAdjust3d"):
                 reduce_stage(os.path.join(src, "stage_rank0", f), os.path.join(sd, f))
         print(dst, f"{sum(os.path.getsize(os.path.join(dp, f)) for dp, _, fs in os.walk(dst) for f in fs) / 1e6:.1f} MB")
