@@ -597,7 +597,7 @@ struct Fields4 {
 // (plane-for-plane copy of the field) and copied back by this launch once every strip is done.
 void unpark_rows(const fv3_ctx *ctx, cudaStream_t st, Fields4 fl, int nf, double *side0, int nk) {
   const fv3_geom g = ctx->g;
-  const fv3::StripGeom sg = fv3::strip_geometry(g, fv3::FVTP_PLANES);
+  const fv3::StripGeom sg = fv3::strip_geometry(g, fv3::FVTP_PLANES, nk);
   if (sg.ns <= 1) return;
   const int64_t side_stride = g.ss * g.n_sub;
   const int h = g.halo, R = sg.rows_per_strip;
@@ -827,7 +827,7 @@ int fv3_d_sw(fv3_ctx *ctx, double *delpc, double *delp, double *pt, double *u, d
 #undef DSW_WINDS
     if (rc) return rc;
     // the parked first u row of every strip but the first
-    const fv3::StripGeom sg = fv3::strip_geometry(g, fv3::FVTP_PLANES);
+    const fv3::StripGeom sg = fv3::strip_geometry(g, fv3::FVTP_PLANES, nz);
     if (sg.ns > 1) {
       const int R = sg.rows_per_strip;
       fv3::launch3d(ctx, st, isc, iec + 1, 0, sg.ns - 1, 0, nz, FV_LAMBDA(int s, int i, int bnd, int k) { FV_DEV_GM

@@ -132,7 +132,7 @@ int fv3_tracer_subcycle(fv3_ctx *ctx, double *const *tracers, int nq, double *dp
     fv3::set_error("fv3_tracer_subcycle: at most 16 tracers");
     return -1;
   }
-  const fv3::StripGeom sg = fv3::strip_geometry(g, FVTP_PLANES);
+  const fv3::StripGeom sg = fv3::strip_geometry(g, FVTP_PLANES, g.nz);
   double *side0 = fv3::scratch_field(ctx, 0);
   const int64_t side_stride = g.ss * g.n_sub;
   int rc = fv3::launch_planes(ctx, (cudaStream_t)stream, 0, g.nz, FVTP_PLANES, FV_LAMBDA(int s, int k, const fv3::Block &b) { FV_DEV_GM

@@ -141,22 +141,54 @@ struct StripGeom {
   int ns, rows_per_strip, res_rows;  // strips per plane, owned rows per strip, resident rows per strip
 };
 
-// strips per plane for a kernel with n_planes shared planes; ns == 0: does not fit
-inline StripGeom strip_geometry(const fv3_geom &g, int n_planes) {
+// strips per plane for a kernel with n_planes shared planes that runs nk levels; ns == 0: does not fit.
+// The smallest number of strips that lets two CTAs share an SM — unless one strip more fills the waves of a SMALL grid
+// better: with few subdomains per GPU (4 or 8 GPUs) nk * n_sub * ns CTAs are only a few waves over the 2 * SMs resident
+// slots, and the cost of the launch is ~ ceil(waves) * (resident rows per CTA).  Every caller of one stage must pass the
+// same (n_planes, nk): the parked-row bookkeeping of the in-place updates depends on the geometry.
+inline StripGeom strip_geometry(const fv3_geom &g, int n_planes, int nk = 0) {
   static int forced = -1;
   if (forced < 0) {
     const char *e = getenv("FV3_FORCE_STRIPS");  // tests: exercise the strip logic on small subdomains
     forced = e ? atoi(e) : 0;
   }
+  auto geom_of = [&](int ns, StripGeom &sg) {
+    const int r = (g.ny + ns - 1) / ns, res = (r + 2 * g.halo + 1 < g.nj) ? r + 2 * g.halo + 1 : g.nj;
+    if (r < 4) return -1;
+    const int64_t bytes = ((int64_t)n_planes * res * g.sj + PLANE_PAD_FRONT + plane_pad_back(g.sj)) * 8;
+    sg = StripGeom{(g.ny + r - 1) / r, r, res};
+    return (forced > 0 || bytes <= PLANE_SMEM_BUDGET) ? 1 : 0;
+  };
   StripGeom sg{0, 0, 0};
   for (int ns = forced > 0 ? forced : 1; ns <= g.ny; ++ns) {
-    const int r = (g.ny + ns - 1) / ns, res = (r + 2 * g.halo + 1 < g.nj) ? r + 2 * g.halo + 1 : g.nj;
-    if (r < 4) break;
-    const int64_t bytes = ((int64_t)n_planes * res * g.sj + PLANE_PAD_FRONT + plane_pad_back(g.sj)) * 8;
-    if (forced > 0 || bytes <= PLANE_SMEM_BUDGET) {
-      sg = StripGeom{(g.ny + r - 1) / r, r, res};
-      break;
+    StripGeom c;
+    const int fit = geom_of(ns, c);
+    if (fit < 0) break;
+    if (fit == 0) continue;
+    sg = c;
+    if (forced <= 0 && nk > 0) {
+      // one strip more, if it fits and costs fewer (rounded-up waves) x (rows per CTA)
+      static int slots = 0;
+      if (slots == 0) {
+#ifdef FV3_HOSTSIM
+        slots = 296;
+#else
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        slots = 2 * sms;
+#endif
+      }
+      StripGeom d;
+      if (geom_of(ns + 1, d) == 1) {
+        auto cost = [&](const StripGeom &x) {
+          const int64_t ctas = (int64_t)nk * g.n_sub * x.ns;
+          return ((ctas + slots - 1) / slots) * x.res_rows;
+        };
+        if (cost(d) * 100 < cost(sg) * 97) sg = d;  // at least 3 % better by the model
+      }
     }
+    break;
   }
   return sg;
 }
@@ -221,7 +253,7 @@ __global__ void __launch_bounds__(PLANE_THREADS, 2) kplane(F f, int k0, int rows
 template <class F>
 inline int launch_planes(const fv3_ctx *ctx, cudaStream_t st, int k0, int k1, int n_planes, F f) {
   if (k1 <= k0) return 0;
-  const StripGeom sg = strip_geometry(ctx->g, n_planes);
+  const StripGeom sg = strip_geometry(ctx->g, n_planes, k1 - k0);
   if (sg.ns == 0) {
     set_error("launch_planes: no strip decomposition of the plane fits in shared memory");
     return -1;

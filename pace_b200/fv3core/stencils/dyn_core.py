@@ -142,11 +142,12 @@ class AcousticDynamics:
 
     def _zero_data(self, state, first_timestep: bool):
         """zero_data (dyn_core.py:48-80)"""
-        for q in (state.mfxd, state.mfyd, state.cxd, state.cyd):
-            q.data.zero_()
+        import torch
+
+        fields = [state.mfxd, state.mfyd, state.cxd, state.cyd]
         if first_timestep:  # domain_full, as the reference
-            self._heat_source.data.zero_()
-            state.diss_estd.data.zero_()
+            fields += [self._heat_source, state.diss_estd]
+        torch._foreach_zero_([q.data for q in fields])   # one multi-tensor launch instead of one fill per field
 
     def __call__(self, state, timestep: float, n_map=1):
         rt, cfg, hu = self._rt, self.config, self._halo_updaters
