@@ -86,7 +86,21 @@ int fv3_update_dz_c(fv3_ctx *ctx, const double *zs, const double *ut, const doub
     double below = gzn[c0 + (int64_t)nz * g.sk];
     gz[c0 + (int64_t)nz * g.sk] = below;
     ws[O2(s, i, j)] = (zs[O2(s, i, j)] - below) * rdt;
-    for (int k = nz - 1; k >= 0; --k) {
+    // the column walk is a dependent max-chain; its loads are not: 8 levels are fetched per trip before the chain runs
+    // (with few subdomains per GPU there are too few columns to hide an L2 latency per level)
+    int k = nz - 1;
+    for (; k - 7 >= 0; k -= 8) {
+      double v[8];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) v[n] = gzn[c0 + (int64_t)(k - n) * g.sk];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        const double kp1 = below + DZ_MIN;
+        below = v[n] > kp1 ? v[n] : kp1;
+        gz[c0 + (int64_t)(k - n) * g.sk] = below;
+      }
+    }
+    for (; k >= 0; --k) {
       const double v = gzn[c0 + (int64_t)k * g.sk], kp1 = below + DZ_MIN;
       below = v > kp1 ? v : kp1;
       gz[c0 + (int64_t)k * g.sk] = below;
@@ -118,7 +132,18 @@ int fv3_gz_from_delz(fv3_ctx *ctx, const double *zs, const double *delz, double 
     const int64_t c0 = O3(s, i, j, 0);
     double v = zs[O2(s, i, j)];
     gz[c0 + (int64_t)nz * g.sk] = v;
-    for (int k = nz - 1; k >= 0; --k) {
+    int k = nz - 1;
+    for (; k - 7 >= 0; k -= 8) {
+      double d[8];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) d[n] = delz[c0 + (int64_t)(k - n) * g.sk];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        v = v - d[n];
+        gz[c0 + (int64_t)(k - n) * g.sk] = v;
+      }
+    }
+    for (; k >= 0; --k) {
       v = v - delz[c0 + (int64_t)k * g.sk];
       gz[c0 + (int64_t)k * g.sk] = v;
     }
@@ -134,7 +159,18 @@ int fv3_pem_from_delp(fv3_ctx *ctx, const double *delp, double *pem, double ptop
     const int64_t c0 = O3(s, i, j, 0);
     double v = ptop;
     pem[c0] = v;
-    for (int k = 1; k < nz; ++k) {  // the reference stencil runs on nz levels and adds delp of the SAME level
+    int k = 1;  // the reference stencil runs on nz levels and adds delp of the SAME level
+    for (; k + 8 <= nz; k += 8) {
+      double d[8];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) d[n] = delp[c0 + (int64_t)(k + n) * g.sk];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        v = v + d[n];
+        pem[c0 + (int64_t)(k + n) * g.sk] = v;
+      }
+    }
+    for (; k < nz; ++k) {
       v = v + delp[c0 + (int64_t)k * g.sk];
       pem[c0 + (int64_t)k * g.sk] = v;
     }

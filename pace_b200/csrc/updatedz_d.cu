@@ -62,24 +62,37 @@ int fv3_update_dz_d(fv3_ctx *ctx, const double *surface_height, double *height, 
                        nullptr, 0, nz + 1, stream)))
     return rc;
   if ((rc = fv3_delnflux_nosg(ctx, height, gx, gy, damp_col, nord_col, nmax, nz + 1, stream))) return rc;
-  // apply_height_fluxes (updatedzd.py:70-126): compute domain, BACKWARD monotonicity fix
+  // apply_height_fluxes (updatedzd.py:70-126): compute domain.  The flux-form update of every level is independent and
+  // runs level-parallel (into a scratch field); only the BACKWARD
+  // monotonicity fix is a column walk, with its loads fetched 8 levels ahead of the dependent max-chain.
+  double *hraw = fv3::scratch_field(ctx, 24);
+  fv3::launch3d(ctx, st, isc, iec + 1, jsc, jec + 1, 0, nz + 1, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
+    const int64_t o = O3(s, i, j, k);
+    const double ar = m.area[O2(s, i, j)];
+    const double area_after = ((ar + xfx_i[o] - xfx_i[o + 1]) + (ar + yfx_i[o] - yfx_i[o + sj])) - ar;
+    hraw[o] = (height[o] * ar + fx[o] - fx[o + 1] + fy[o] - fy[o + sj]) / area_after + (gx[o] - gx[o + 1] + gy[o] - gy[o + sj]) / ar;
+  });
   fv3::launch2d(ctx, st, isc, iec + 1, jsc, jec + 1, FV_LAMBDA(int s, int i, int j) { FV_DEV_GM
     const int64_t c0 = O3(s, i, j, 0), sk = g.sk;
-    const double ar = m.area[O2(s, i, j)];
-    double below = 0.0;
-    for (int k = nz; k >= 0; --k) {
-      const int64_t o = c0 + k * sk;
-      const double area_after = ((ar + xfx_i[o] - xfx_i[o + 1]) + (ar + yfx_i[o] - yfx_i[o + sj])) - ar;
-      double hv = (height[o] * ar + fx[o] - fx[o + 1] + fy[o] - fy[o + sj]) / area_after +
-                  (gx[o] - gx[o + 1] + gy[o] - gy[o + sj]) / ar;
-      if (k == nz) {
-        ws[O2(s, i, j)] = (surface_height[O2(s, i, j)] - hv) / dt;
-      } else {
+    double below = hraw[c0 + nz * sk];
+    ws[O2(s, i, j)] = (surface_height[O2(s, i, j)] - below) / dt;
+    height[c0 + nz * sk] = below;
+    int k = nz - 1;
+    for (; k - 7 >= 0; k -= 8) {
+      double v[8];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) v[n] = hraw[c0 + (k - n) * sk];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
         const double other = below + DZ_MIN;
-        hv = hv > other ? hv : other;
+        below = v[n] > other ? v[n] : other;
+        height[c0 + (k - n) * sk] = below;
       }
-      height[o] = hv;
-      below = hv;
+    }
+    for (; k >= 0; --k) {
+      const double hv = hraw[c0 + k * sk], other = below + DZ_MIN;
+      below = hv > other ? hv : other;
+      height[c0 + k * sk] = below;
     }
   });
   return fv3::check_launch("fv3_update_dz_d");
