@@ -86,6 +86,19 @@ class DynamicalCore:
             self.checkpointer(f"FVDynamics-{tag}", u=state.u, v=state.v, w=state.w, delz=state.delz, va=state.va,
                               uc=state.uc, vc=state.vc, qvapor=state.qvapor)
 
+    def _checkpoint_remapping(self, state, tag):
+        """Remapping-In / Remapping-Out (fv_dynamics.py:340-395); te_2d is left out (consv_te = 0 never fills it), pe and
+        peln are handed over in this repo's (i, j, k) order, not the Fortran (i, k, j) the reference transposes to."""
+        if not self.call_checkpointer:
+            return
+        common = dict(pt=state.pt, delp=state.delp, delz=state.delz, peln=state.peln, u=state.u, v=state.v, w=state.w,
+                      cappa=self._cappa, pk=state.pk, pe=state.pe, dp1=self._dp_initial)
+        if tag == "In":
+            self.checkpointer("Remapping-In", ua=state.ua, va=state.va, phis=state.phis, ps=state.ps, wsd=self._wsd,
+                              omga=state.omga, **common)
+        else:
+            self.checkpointer("Remapping-Out", pkz=state.pkz, **common)
+
     def _check_bound_state(self, state):
         """The tracer pointer table, the tracer dictionary and every halo updater are bound to the DycoreState given at
         construction (the reference binds its halo updaters the same way, dyn_core.py:273-343).  A different state
@@ -152,11 +165,13 @@ class DynamicalCore:
                                       cxd=state.cxd, cyd=state.cyd)
             if rt.comm.geometry.nz > 4:
                 with timer.clock("Remapping"):
+                    self._checkpoint_remapping(state, "In")
                     self._lagrangian_to_eulerian_obj(
                         self.tracers, state.pt, state.delp, state.delz, state.peln, state.u, state.v, state.w,
                         self._cappa, state.q_con, state.qcld, state.pkz, state.pk, state.pe, state.phis, state.ps,
                         self._wsd, None, None, self._dp_initial, self._ptop, c.KAPPA, c.ZVIR, last_step,
                         self.config.consv_te, self._timestep / self._k_split)
+                    self._checkpoint_remapping(state, "Out")
                 if last_step:
                     rt.call("fv3_omega_from_w", state.delp.ptr, state.delz.ptr, state.w.ptr, state.omga.ptr)
                     if self.config.nf_omega > 0:

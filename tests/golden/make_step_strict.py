@@ -54,6 +54,42 @@ def c12k2n6():
     print(dst, f"{size(dst):.1f} MB")
 
 
+# savepoint variable -> key in the reference's stage capture (oracle/refshim/runner.py wraps each stage's __call__)
+CHECKPOINTS = {
+    "Tracer2D1L-In": ("Tracer2D1L", "in", dict(dp1="dp1", mfxd="x_mass_flux", mfyd="y_mass_flux", cxd="x_courant", cyd="y_courant")),
+    "Tracer2D1L-Out": ("Tracer2D1L", "out", dict(dp1="dp1", mfxd="x_mass_flux", mfyd="y_mass_flux", cxd="x_courant", cyd="y_courant",
+                                                 **{t: "tracers." + t for t in TRACERS})),
+    "Remapping-In": ("Remapping", "in", {n: n for n in ("pt", "delp", "delz", "peln", "u", "v", "w", "cappa", "pk", "pe", "ps", "wsd", "dp1")}),
+    "Remapping-Out": ("Remapping", "out", {n: n for n in ("pt", "delp", "delz", "peln", "u", "v", "w", "cappa", "pkz", "pk", "pe", "dp1")}),
+    # ucd, vcd and divgdd are left out: the reference's d_sw uses uc, vc and divgd as work arrays, what they hold on
+    # exit is scratch that nothing reads (c_sw rewrites all three)
+    "D_SW-Out": ("D_SW", "out", dict(wd="w", delpd="delp", ud="u", vd="v", ptd="pt", uad="ua", vad="va",
+                                     xfxd="xfx", yfxd="yfx", mfxd="mfx", mfyd="mfy")),
+}
+CHECKPOINT_CALLS = {"Tracer2D1L": (0, 1), "Remapping": (0, 1), "D_SW": (0, 7, 11)}
+
+
+def c12k2n6_checkpoints():
+    """In-flight savepoints of the k_split=2, n_split=6 run, rank 0: the arguments the reference's TracerAdvection,
+    LagrangianToEulerian and DGridShallowWaterLagrangianDynamics calls entered / left with, cropped to the compute
+    domain (+1 for staggered fields) on a level subsample -> tests/golden/c12k2n6_step/checkpoints_rank0.npz, keyed
+    "<savepoint>#<call>/<variable>" with the savepoint and variable names of the reference's checkpointer calls
+    (fv_dynamics.py:340-422, dyn_core.py:608-668)."""
+    src, dst = os.path.join(CACHE, "c12k2n6", "stage_rank0"), os.path.join(HERE, "c12k2n6_step")
+    out = {}
+    for sp, (stage, side, names) in CHECKPOINTS.items():
+        for call in CHECKPOINT_CALLS[stage]:
+            z = np.load(os.path.join(src, f"{stage}#{call}.npz"))
+            for var, key in names.items():
+                a = z[f"{side}.{key}"]
+                a = a[3:16, 3:16]
+                if a.ndim == 3:
+                    a = a[:, :, [k for k in LEVELS if k < (80 if key in ("pe", "peln", "pk") else 79)]]
+                out[f"{sp}#{call}/{var}"] = np.ascontiguousarray(a)
+    np.savez_compressed(os.path.join(dst, "checkpoints_rank0.npz"), levels=np.array(LEVELS), **out)
+    print(os.path.join(dst, "checkpoints_rank0.npz"), f"{os.path.getsize(os.path.join(dst, 'checkpoints_rank0.npz')) / 1e6:.1f} MB")
+
+
 def c24L2():
     src = os.path.join(CACHE, "c24L2k2n3")
     inp, dst = os.path.join(HERE, "c24L2_inputs"), os.path.join(HERE, "c24L2k2n3_step")
@@ -130,5 +166,6 @@ if __name__ == "__main__":
     c12_sat()
     if os.path.exists(os.path.join(CACHE, "c12k2n6", "meta.json")):
         c12k2n6()
+        c12k2n6_checkpoints()
     if os.path.exists(os.path.join(CACHE, "c24L2k2n3", "meta.json")):
         c24L2()

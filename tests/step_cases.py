@@ -69,7 +69,7 @@ def load(case):
     return meta, grids, s0, s1
 
 
-def build(meta, grids, s0, dev=None, process_comm=None):
+def build(meta, grids, s0, dev=None, process_comm=None, checkpointer=None):
     """`process_comm`: several processes (GPUs) share the case; grids / s0 are then sliced to the local subdomains."""
     from pace_b200.fv3core._config import baroclinic_config
     from pace_b200.fv3core.dycore_state import DycoreState
@@ -93,7 +93,8 @@ def build(meta, grids, s0, dev=None, process_comm=None):
     rt = Runtime(comm, qf, gd, damp, cfg)
     sf = StencilFactory(None, GridIndexing.from_sizer_and_communicator(qf.sizer, comm), rt)
     state = DycoreState.init_from_numpy_arrays(s0, qf)
-    dycore = DynamicalCore(comm, gd, sf, qf, damp, cfg, state.phis, state, timedelta(seconds=cfg.dt_atmos))
+    dycore = DynamicalCore(comm, gd, sf, qf, damp, cfg, state.phis, state, timedelta(seconds=cfg.dt_atmos),
+                           checkpointer=checkpointer)
     return dycore, state
 
 
