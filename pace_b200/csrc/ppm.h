@@ -16,7 +16,16 @@ constexpr double PPM_P1 = 7.0 / 12.0, PPM_P2 = -1.0 / 12.0;
 constexpr double PPM_S11 = 11.0 / 14.0, PPM_S14 = 4.0 / 7.0, PPM_S15 = 3.0 / 14.0;
 
 // basic_operations.sign (basic_operations.py:32-39): +|a| only for b > 0
-FV_HD double rsign(double a, double b) { return b > 0 ? fabs(a) : -fabs(a); }
+// On the device the sign bit is set directly (one compare, one select, one logic op instead of two negations, a
+// compare and two selects); the value is the same bit for bit, signed zeros and NaN operands included.
+FV_HD double rsign(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  const int hi = (__double2hiint(a) & 0x7fffffff) | (b > 0 ? 0 : (int)0x80000000);
+  return __hiloint2double(hi, __double2loint(a));
+#else
+  return b > 0 ? fabs(a) : -fabs(a);
+#endif
+}
 
 struct Edge1D {
   bool lo, hi;     // subdomain touches the low / high tile edge in this direction
