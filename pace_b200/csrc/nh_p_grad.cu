@@ -22,39 +22,48 @@ int fv3_nh_p_grad(fv3_ctx *ctx, double *u, double *v, double *pp, double *gz, do
   double *wk1 = fv3::scratch_field(ctx, 19);
   const double top_value = pow(ptop, akap);  // host libm, as `ptop ** akap` in the reference (:219)
   // four A->B interpolations (nh_p_grad.py:221-224) + set_k0 (:11-20): one plane-resident kernel per level
-  int rc = fv3::launch_planes(ctx, st, 0, nz + 1, 4, FV_LAMBDA(int s, int k, const fv3::Block &b) { FV_DEV_GM
-    double *SQ = b.plane(0), *QX = b.plane(1), *QY = b.plane(2), *OUT = b.plane(3);
+  // Five planes: the A-grid input is double-buffered — the next field's rows arrive by one bulk (TMA) copy while the
+  // current field is interpolated, so no phase of the CTA waits on a load it has just issued.
+  int rc = fv3::launch_planes(ctx, st, 0, nz + 1, 5, FV_LAMBDA(int s, int k, const fv3::Block &b) { FV_DEV_GM
+    double *SQ0 = b.plane(0), *QX = b.plane(1), *QY = b.plane(2), *OUT = b.plane(3), *SQ1 = b.plane(4);
     const int64_t ob = O3(s, 0, 0, k);
     const int sj2 = g.sj, h2 = g.halo;
-    auto store = [&](double *dst) {
-      b.rect(h2, h2 + g.nx + 1, b.ja, b.jtop() + 1, [&](int i, int j) {
-        const int p = j * sj2 + i;
-        dst[ob + p] = OUT[p];
-      });
-    };
     auto fill = [&](double *dst, double value) {
       b.rect(h2, h2 + g.nx + 1, b.ja, b.jtop() + 1, [&](int i, int j) { dst[ob + j * sj2 + i] = value; });
     };
     b.prefetch_next_wave(gz, g, k);
-    if (k >= 1) {
-      b.prefetch_rows(pp + ob, sj2);
-      b.prefetch_rows(pk3 + ob, sj2);
+    // fields of this interface level: gz always, pp and pk3 below the top interface, delp on layers
+    const int nf = 1 + (k >= 1 ? 2 : 0) + (k < nz ? 1 : 0);
+    auto field = [&](int f, const double *&src, double *&dst) {
+      const int id = f == 0 ? 0 : (k >= 1 ? f : 3);  // 0 gz, 1 pp, 2 pk3, 3 delp
+      src = id == 0 ? gz : id == 1 ? pp : id == 2 ? pk3 : delp;
+      dst = id == 0 ? gzb : id == 1 ? ppb : id == 2 ? pk3b : wk1;
+    };
+    const double *src, *nxt;
+    double *dst, *unused;
+    field(0, src, dst);
+    b.bulk_begin(1, sj2);
+    b.bulk_rows(SQ0, src + ob, sj2);
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+      if (f >= nf) break;
+      double *SQ = (f & 1) ? SQ1 : SQ0;
+      field(f, src, dst);
+      b.bulk_wait();
+      if (f + 1 < nf) {
+        field(f + 1, nxt, unused);
+        b.bulk_begin(1, sj2);
+        b.bulk_rows((f & 1) ? SQ0 : SQ1, nxt + ob, sj2);
+      }
+      fv3::a2b_plane(g, m, s, b, src + ob, SQ, QX, QY, OUT, true);
+      b.rect(h2, h2 + g.nx + 1, b.ja, b.jtop() + 1, [&](int i, int j) {
+        const int p = j * sj2 + i;
+        dst[ob + p] = OUT[p];
+      });
     }
-    if (k < nz) b.prefetch_rows(delp + ob, sj2);
-    fv3::a2b_plane(g, m, s, b, gz + ob, SQ, QX, QY, OUT);
-    store(gzb);
-    if (k >= 1) {
-      fv3::a2b_plane(g, m, s, b, pp + ob, SQ, QX, QY, OUT);
-      store(ppb);
-      fv3::a2b_plane(g, m, s, b, pk3 + ob, SQ, QX, QY, OUT);
-      store(pk3b);
-    } else {
+    if (k < 1) {
       fill(ppb, 0.0);
       fill(pk3b, top_value);
-    }
-    if (k < nz) {
-      fv3::a2b_plane(g, m, s, b, delp + ob, SQ, QX, QY, OUT);
-      store(wk1);
     }
   });
   if (rc) return rc;

@@ -1,6 +1,7 @@
 // Height of the Lagrangian surfaces on the D grid.
 //   fv3_update_dz_d <- UpdateHeightOnDGrid.__call__ (fv3core/pace/fv3core/stencils/updatedzd.py:283-356)
 #include "common.h"
+#include "fdiv.h"
 
 extern "C" int fv3_fvtp2d(fv3_ctx *, const double *, const double *, const double *, const double *, const double *,
                           double *, double *, const double *, const double *, const double *, int, const double *,
@@ -43,7 +44,26 @@ int fv3_update_dz_d(fv3_ctx *ctx, const double *surface_height, double *height, 
       const double xt1 = 2.0 * gk[0] * (gk[0] + 1.0);
       col[0] = (xt1 * qc[c0] + qc[c0 + sk]) / beta[0];
     }
-    for (int k = 1; k < nz; ++k) col[k] = (3.0 * (qc[c0 + (k - 1) * sk] + gk[k] * qc[c0 + k * sk]) - col[k - 1]) / beta[k];
+    // forward elimination: one dependent divide per level.  The reciprocals of beta (the same for every column) are
+    // refined four levels at a time AHEAD of the chain, which then costs a multiply and two FMAs per level (fdiv.h)
+    int k = 1;
+    double prev = col[0];
+    for (; k + 3 < nz; k += 4) {
+      fv3::Recip rb[4];
+      double rhs[4], qv[5];
+#pragma unroll
+      for (int n = 0; n < 4; ++n) rb[n] = fv3::recip_of(beta[k + n]);
+#pragma unroll
+      for (int n = 0; n < 5; ++n) qv[n] = qc[c0 + (k - 1 + n) * sk];
+#pragma unroll
+      for (int n = 0; n < 4; ++n) rhs[n] = 3.0 * (qv[n] + gk[k + n] * qv[n + 1]);
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        prev = fv3::div_by(rhs[n] - prev, rb[n]);
+        col[k + n] = prev;
+      }
+    }
+    for (; k < nz; ++k) col[k] = (3.0 * (qc[c0 + (k - 1) * sk] + gk[k] * qc[c0 + k * sk]) - col[k - 1]) / beta[k];
     {
       const double gl = gk[nz - 1];
       const double a_bot = 1.0 + gl * (gl + 1.5);
@@ -52,9 +72,25 @@ int fv3_update_dz_d(fv3_ctx *ctx, const double *surface_height, double *height, 
       col[nz] = (xt1 * qc[c0 + (nz - 1) * sk] + qc[c0 + (nz - 2) * sk] - a_bot * col[nz - 1]) / xt2;
     }
     qi[c0 + nz * sk] = col[nz];
-    for (int k = nz - 1; k >= 0; --k) {
-      col[k] = col[k] - gamma[k] * col[k + 1];
-      qi[c0 + k * sk] = col[k];
+    // back substitution: partial solutions and gammas fetched 8 levels ahead of the multiply-subtract chain
+    double above = col[nz];
+    int kb = nz - 1;
+    for (; kb - 7 >= 0; kb -= 8) {
+      double cv[8], gv[8];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        cv[n] = col[kb - n];
+        gv[n] = gamma[kb - n];
+      }
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        above = cv[n] - gv[n] * above;
+        qi[c0 + (kb - n) * sk] = above;
+      }
+    }
+    for (; kb >= 0; --kb) {
+      above = col[kb] - gamma[kb] * above;
+      qi[c0 + kb * sk] = above;
     }
   });
   int rc;
