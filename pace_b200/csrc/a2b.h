@@ -5,6 +5,7 @@
 //                a2b_interpolation (:453-481).
 #pragma once
 #include "common.h"
+#include "plane.h"
 
 namespace fv3 {
 
@@ -135,14 +136,15 @@ FV_DEV void a2b_plane(const fv3_geom &g, const fv3_grid &m, int s, const B &b, c
   // The two columns (rows) either side of a tile edge use the one-sided formulas (divides, metric loads): they are
   // separate, densely packed tasks of the same phase instead of a few slow lanes in every warp of the bulk pass.
   const int nbx = nxc * nxr, nby = nxw * nyr, nex = 4 * nxr, ney = 4 * nxw;
+  const float inv_c = 1.0f / (float)nxc, inv_w = 1.0f / (float)nxw;
   b.par(nbx + nby + nex + ney, [&](int t) {
     if (t < nbx) {
-      const int jr = t / nxc, i = isc + (t - jr * nxc), j = xj0 + jr;
+      const int jr = row_of(t, nxc, inv_c), i = isc + (t - jr * nxc), j = xj0 + jr;
       if (i <= isc + 1 || i >= iec) return;
       QX[j * sj + i] = A2B::b2 * (q(i - 2, j) + q(i + 1, j)) + A2B::b1 * (q(i - 1, j) + q(i, j));
     } else if (t < nbx + nby) {
       const int t2 = t - nbx;
-      const int jr = t2 / nxw, i = isc - 2 + (t2 - jr * nxw), j = yj0 + jr;
+      const int jr = row_of(t2, nxw, inv_w), i = isc - 2 + (t2 - jr * nxw), j = yj0 + jr;
       if (j <= jsc + 1 || j >= jec) return;
       QY[j * sj + i] = A2B::b2 * (q(i, j - 2) + q(i, j + 1)) + A2B::b1 * (q(i, j - 1) + q(i, j));
     } else if (t < nbx + nby + nex) {
@@ -152,7 +154,7 @@ FV_DEV void a2b_plane(const fv3_geom &g, const fv3_grid &m, int s, const B &b, c
       QX[j * sj + i] = a2b_qx(g, m, s, q, i, j);
     } else {
       const int t2 = t - nbx - nby - nex;
-      const int c = t2 / nxw, i = isc - 2 + (t2 - c * nxw), j = c < 2 ? jsc + c : jec + (c - 2);
+      const int c = row_of(t2, nxw, inv_w), i = isc - 2 + (t2 - c * nxw), j = c < 2 ? jsc + c : jec + (c - 2);
       if (c >= 2 && j <= jsc + 1) return;
       if (j < yj0 || j >= yj1) return;
       QY[j * sj + i] = a2b_qy(g, m, s, q, i, j);

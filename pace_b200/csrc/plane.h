@@ -28,6 +28,18 @@ constexpr int PLANE_PAD_FRONT = 16;
 FV_HD int plane_pad_back(int sj) { return 2 * sj + 16; }
 constexpr int PLANE_SMEM_BUDGET = (233472 / 2) - 1024;  // bytes per CTA for two CTAs per SM (228 KB, 1 KB reserved each)
 
+// t / w for the index decode of a block-wide pass without an integer division (20+ instructions per point): exact for
+// t < 2^20, w < 2^10 (every plane that fits in shared memory); `inv` = 1.0f / w
+FV_HD int row_of(int t, int w, float inv) {
+#ifdef FV3_HOSTSIM
+  (void)inv;
+  return t / w;
+#else
+  (void)w;
+  return (int)(((float)t + 0.5f) * inv);
+#endif
+}
+
 struct Block {
   double *sm;
   int pl, off;  // doubles per shared plane; r0 * sj
