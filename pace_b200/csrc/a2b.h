@@ -117,10 +117,12 @@ FV_HD double a2b_edge_value(const fv3_geom &g, const fv3_grid &m, int s, Q q, in
 // in shared memory instead of being re-derived inside every thread.
 //   SQ: qin plane   QX / QY: ppm_volume_mean_x / _y   OUT: B-grid result (tile-edge values first, then the rest)
 // qin is a global pointer to the start of the (s, k) plane; the arrays are shared planes of the block (Block::plane).
-// On return OUT holds the corner rows [ja, jb] of the strip.
+// On return OUT holds the corner rows [ja, jb] of the strip — or, with `gout` (start of a global (s, k) plane), the
+// rows the strip owns ([ja, jtop]) are written there directly and OUT keeps only the tile-edge values.
+// Two block-wide passes: (1) qx, qy and the tile-edge values, all functions of qin only; (2) the interpolation.
 template <class B>
 FV_DEV void a2b_plane(const fv3_geom &g, const fv3_grid &m, int s, const B &b, const double *qin, double *SQ, double *QX,
-                     double *QY, double *OUT, bool loaded = false) {
+                     double *QY, double *OUT, bool loaded = false, double *gout = nullptr) {
   const int sj = g.sj, h = g.halo;
   const int isc = h, iec = h + g.nx - 1, jsc = h, jec = h + g.ny - 1;
   const bool W = on_west(g, s), E = on_east(g, s), S = on_south(g, s), N = on_north(g, s);
@@ -136,8 +138,12 @@ FV_DEV void a2b_plane(const fv3_geom &g, const fv3_grid &m, int s, const B &b, c
   // The two columns (rows) either side of a tile edge use the one-sided formulas (divides, metric loads): they are
   // separate, densely packed tasks of the same phase instead of a few slow lanes in every warp of the bulk pass.
   const int nbx = nxc * nxr, nby = nxw * nyr, nex = 4 * nxr, ney = 4 * nxw;
+  // tile-edge values, one corner row beyond the strip (the rows next to a tile edge read them): the points of the west /
+  // east corner columns and of the south / north corner rows are tasks of the same pass
+  const int ej0 = b.lo(jsc, 1), ej1 = b.hi(jec + 2, 2), ner = ej1 > ej0 ? ej1 - ej0 : 0;
+  const int nev = (W || E || S || N) ? 2 * ner + 2 * nxc : 0;
   const float inv_c = 1.0f / (float)nxc, inv_w = 1.0f / (float)nxw;
-  b.par(nbx + nby + nex + ney, [&](int t) {
+  b.par(nbx + nby + nex + ney + nev, [&](int t) {
     if (t < nbx) {
       const int jr = row_of(t, nxc, inv_c), i = isc + (t - jr * nxc), j = xj0 + jr;
       if (i <= isc + 1 || i >= iec) return;
@@ -152,20 +158,33 @@ FV_DEV void a2b_plane(const fv3_geom &g, const fv3_grid &m, int s, const B &b, c
       const int c = t2 & 3, j = xj0 + (t2 >> 2), i = c < 2 ? isc + c : iec + (c - 2);
       if (c >= 2 && i <= isc + 1) return;  // tiny domains: column already done as a west column
       QX[j * sj + i] = a2b_qx(g, m, s, q, i, j);
-    } else {
+    } else if (t < nbx + nby + nex + ney) {
       const int t2 = t - nbx - nby - nex;
       const int c = row_of(t2, nxw, inv_w), i = isc - 2 + (t2 - c * nxw), j = c < 2 ? jsc + c : jec + (c - 2);
       if (c >= 2 && j <= jsc + 1) return;
       if (j < yj0 || j >= yj1) return;
       QY[j * sj + i] = a2b_qy(g, m, s, q, i, j);
+    } else {
+      int t2 = t - nbx - nby - nex - ney, i, j;
+      if (t2 < 2 * ner) {  // west, then east corner column
+        const bool east = t2 >= ner;
+        if (east ? !E : !W) return;
+        i = east ? iec + 1 : isc;
+        j = ej0 + (east ? t2 - ner : t2);
+      } else {  // south, then north corner row
+        t2 -= 2 * ner;
+        const bool north = t2 >= nxc;
+        if (north ? !N : !S) return;
+        j = north ? jec + 1 : jsc;
+        if (j < ej0 || j >= ej1) return;
+        i = isc + (north ? t2 - nxc : t2);
+      }
+      const double v = a2b_edge_value(g, m, s, q, i, j);
+      OUT[j * sj + i] = v;  // a tile-corner point is visited by a column and a row task: same value
+      if (gout && j >= ja && j <= b.jtop()) gout[j * sj + i] = v;
     }
   });
-  // tile-edge values, one corner row beyond the strip (the rows next to a tile edge read them)
-  b.rect(isc, iec + 2, b.lo(jsc, 1), b.hi(jec + 2, 2), [&](int i, int j) {
-    if ((W && i == isc) || (E && i == iec + 1) || (S && j == jsc) || (N && j == jec + 1))
-      OUT[j * sj + i] = a2b_edge_value(g, m, s, q, i, j);
-  });
-  b.rect(isc, iec + 2, ja, jb + 1, [&](int i, int j) {
+  b.rect(isc, iec + 2, ja, (gout ? b.jtop() : jb) + 1, [&](int i, int j) {
     if ((W && i == isc) || (E && i == iec + 1) || (S && j == jsc) || (N && j == jec + 1)) return;
     auto qx = [&](int jj) { return QX[jj * sj + i]; };
     auto qy = [&](int ii) { return QY[j * sj + ii]; };
@@ -188,7 +207,10 @@ FV_DEV void a2b_plane(const fv3_geom &g, const fv3_grid &m, int s, const B &b, c
     } else {
       qyy = A2B::a2 * (qy(i - 2) + qy(i + 1)) + A2B::a1 * (qy(i - 1) + qy(i));
     }
-    OUT[j * sj + i] = 0.5 * (qxx + qyy);
+    if (gout)
+      gout[j * sj + i] = 0.5 * (qxx + qyy);
+    else
+      OUT[j * sj + i] = 0.5 * (qxx + qyy);
   });
 }
 

@@ -55,11 +55,7 @@ int fv3_nh_p_grad(fv3_ctx *ctx, double *u, double *v, double *pp, double *gz, do
         b.bulk_begin(1, sj2);
         b.bulk_rows((f & 1) ? SQ0 : SQ1, nxt + ob, sj2);
       }
-      fv3::a2b_plane(g, m, s, b, src + ob, SQ, QX, QY, OUT, true);
-      b.rect(h2, h2 + g.nx + 1, b.ja, b.jtop() + 1, [&](int i, int j) {
-        const int p = j * sj2 + i;
-        dst[ob + p] = OUT[p];
-      });
+      fv3::a2b_plane(g, m, s, b, src + ob, SQ, QX, QY, OUT, true, dst + ob);  // B-grid values straight to the scratch field
     }
     if (k < 1) {
       fill(ppb, 0.0);
