@@ -92,6 +92,10 @@ inline
 template <int MORD, bool XDIR, class Fin>
 struct Sweep {
   const double *Qs, *cg, *dxg;
+  // lines outside [alt_lo, alt_hi] read their values from Qalt instead of Qs (same offsets): the y sweeps of the x-halo
+  // columns of a strip that holds a cube-corner block (transport.h).  Default: no such lines.
+  const double *Qalt;
+  int alt_lo, alt_hi;
   Edge1D e;
   int sj, l0, nl, f0, f1, fv0, fb, ng, nbulk, n;  // n: tasks of this sweep (bulk + tile-edge)
   unsigned nfv;
@@ -100,7 +104,8 @@ struct Sweep {
 
   FV_DEV Sweep(const double *Qs_, int sj_, const double *cg_, const double *dxg_, const Edge1D &e_, int l0_, int nl_, int f0_,
                int f1_, Fin fin_)
-      : Qs(Qs_), cg(cg_), dxg(dxg_), e(e_), sj(sj_), l0(l0_), nl(nl_), f0(f0_), f1(f1_), fin(fin_) {
+      : Qs(Qs_), cg(cg_), dxg(dxg_), Qalt(Qs_), alt_lo(-(1 << 30)), alt_hi(1 << 30), e(e_), sj(sj_), l0(l0_), nl(nl_), f0(f0_),
+        f1(f1_), fin(fin_) {
     constexpr int R = SWEEP_R;
     // faces the edge tasks own (skipped by the bulk tasks); empty ranges away from tile edges
     const int elo1 = e.lo ? e.start + 2 : e.start - 1;  // [e.start, elo1]
@@ -118,6 +123,12 @@ struct Sweep {
     inv = 1.0f / (float)(XDIR ? (ng > 0 ? ng : 1) : (nl > 0 ? nl : 1));
   }
 
+  FV_DEV void set_alt(const double *q, int lo, int hi) {
+    Qalt = q;
+    alt_lo = lo;
+    alt_hi = hi;
+  }
+
   FV_DEV void run(int t) const {
     constexpr int R = SWEEP_R;
     const int st = XDIR ? 1 : sj, ls = XDIR ? sj : 1;
@@ -129,6 +140,7 @@ struct Sweep {
       const int l = l0 + (XDIR ? hi_ : lo_), gi = XDIR ? lo_ : hi_;
       const int F0 = fb + gi * R;
       const int p0 = F0 * st + l * ls;
+      const double *Qs = (l < alt_lo || l > alt_hi) ? Qalt : this->Qs;
       // window w[n] = q[F0 - 4 + n], n = 0..9 (w[0] only completes the aligned pair of an x sweep).  Loads are
       // unconditional: a window may reach into the guard doubles around the planes (plane.h) or a neighbouring row,
       // the faces computed from such values lie outside [fv0, fv1] and are dropped.
@@ -173,6 +185,7 @@ struct Sweep {
       // (line, tile edge) = 3 faces.
       const int t2 = t - nbulk;
       const int l = l0 + (t2 >> 1);
+      const double *Qs = (l < alt_lo || l > alt_hi) ? Qalt : this->Qs;
       const bool high = t2 & 1;
       if (high ? !e.hi : !e.lo) return;
       const int fa = high ? e.end - 1 : e.start;  // faces fa .. fa + 2

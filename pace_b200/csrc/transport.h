@@ -61,31 +61,35 @@ FV_DEV void fvtp2d_plane(const fv3_geom &g, const fv3_grid &m, int s, int k, con
   auto inner_y = make_sweep<MORD, false>(Q, sj, cry, dya, ey, 0, nwi, ja, jb, [&](int p, double val) { A[p] = val; });
   auto inner_x = make_sweep<MORD, true>(Q, sj, crx, dxa, ex, rl, rh - rl, isc, iec + 1, [&](int p, double val) { B[p] = val; });
   if (fix) {
-    b.par(4 * h * h, [&](int t) {
-      const int c = t / (h * h), r = t - c * h * h, a1 = r / h, b1 = r - a1 * h;
-      const int i = (c & 1) ? iec + 1 + a1 : a1, j = (c & 2) ? jec + 1 + b1 : b1;
-      if (j < rl || j >= rh) return;
-      int ii = i, jj = j;
-      corner_y(g, s, ii, jj);
-      if (ii != i || jj != j) Q[j * sj + i] = a.add2d ? q[jj * sj + ii] + a.add2d[jj * sj + ii] : q[jj * sj + ii];
+    // The y sweeps of the x-halo columns want the corner blocks as copy_corners_y leaves them, the x sweeps of the
+    // y-halo rows as copy_corners_x does.  Both forms at once: Q gets the x form, and the 2 x 3 halo columns are
+    // copied into D (free until the transverse updates) with the y form of their corner cells — one small pass; the
+    // y sweep then reads its halo columns from D.
+    const int ncol = 2 * h, nrow = rh - rl;
+    b.par(4 * h * h + ncol * nrow, [&](int t) {
+      if (t < 4 * h * h) {
+        const int c = t / (h * h), r = t - c * h * h, a1 = r / h, b1 = r - a1 * h;
+        const int i = (c & 1) ? iec + 1 + a1 : a1, j = (c & 2) ? jec + 1 + b1 : b1;
+        if (j < rl || j >= rh) return;
+        int ii = i, jj = j;
+        corner_x(g, s, ii, jj);
+        if (ii != i || jj != j) Q[j * sj + i] = a.add2d ? q[jj * sj + ii] + a.add2d[jj * sj + ii] : q[jj * sj + ii];
+      } else {
+        const int t2 = t - 4 * h * h, jr = t2 / ncol, c = t2 - jr * ncol;
+        const int i = c < h ? c : iec + 1 + (c - h), j = rl + jr;
+        int ii = i, jj = j;
+        corner_y(g, s, ii, jj);
+        // a cell of a corner block comes from global memory (Q is being rewritten by the tasks above)
+        if (j < jsc || j > jec)
+          D[j * sj + i] = a.add2d ? q[jj * sj + ii] + a.add2d[jj * sj + ii] : q[jj * sj + ii];
+        else
+          D[j * sj + i] = Q[j * sj + i];
+      }
     });
-    // 2. inner y sweep on q: all columns, faces ja .. jb
-    b.par(inner_y.n, [&](int t) { inner_y.run(t); });
-    // 3. cube-corner blocks as copy_corners_x leaves them
-    b.par(4 * h * h, [&](int t) {
-      const int c = t / (h * h), r = t - c * h * h, a1 = r / h, b1 = r - a1 * h;
-      const int i = (c & 1) ? iec + 1 + a1 : a1, j = (c & 2) ? jec + 1 + b1 : b1;
-      if (j < rl || j >= rh) return;
-      int ii = i, jj = j;
-      corner_x(g, s, ii, jj);
-      Q[j * sj + i] = a.add2d ? q[jj * sj + ii] + a.add2d[jj * sj + ii] : q[jj * sj + ii];
-    });
-    // 4. inner x sweep on q: resident rows, faces isc .. iec+1
-    b.par(inner_x.n, [&](int t) { inner_x.run(t); });
-  } else {
-    // 2 + 4. no corner block in reach: both inner sweeps read the same plane, one pass
-    ppm_sweep_pair(b, inner_y, inner_x);
+    inner_y.set_alt(D, isc, iec);
   }
+  // 2 + 4. both inner sweeps, one pass
+  ppm_sweep_pair(b, inner_y, inner_x);
   // 5. transverse updates: q_i (into Q, owned rows) and q_j (into D, compute columns of the resident rows)
   b.rect(0, nwi, rl, rh, [&](int i, int j) {
     const int p = j * sj + i;
