@@ -2,7 +2,7 @@
 //   fv3_c_sw  <-  CGridShallowWaterDynamics.__call__ (fv3core/pace/fv3core/stencils/c_sw.py:607-766) including
 //                 DGrid2AGrid2CGridVectors.__call__ (d2a2c_vect.py:547-655) and the corner fills it uses
 //                 (stencils/pace/stencils/corners.py:130-304).
-// The reference's 24 stencil launches are regrouped into 8 launches; region-restricted statements become
+// The reference's 24 stencil launches are regrouped into 6 launches; region-restricted statements become
 // per-subdomain tile-edge predicates (geom.edge).  Values, not statement order, are reproduced: every point is
 // computed with the formula that "wins" in the reference's statement sequence.
 #include "common.h"
@@ -64,18 +64,21 @@ int fv3_c_sw(fv3_ctx *ctx, double *delp, double *pt, const double *u, const doub
   const int ied = iec + h, jed = jec + h;
   const int sj = g.sj;
   double *utmp = fv3::scratch_field(ctx, 0), *vtmp = fv3::scratch_field(ctx, 1);
-  double *ke = fv3::scratch_field(ctx, 5), *vort = fv3::scratch_field(ctx, 6);
+  double *ke = fv3::scratch_field(ctx, 5);
+  double *uc0 = fv3::scratch_field(ctx, 2), *vc0 = fv3::scratch_field(ctx, 3);  // d2a2c winds before the update
   int npt = 4;
   if (npt > g.nx - 1 || npt > g.ny - 1) npt = 0;
   const int off = npt == 0 ? -1 : 3;
   const int nord = ctx->c.nord;
 
-  // K1: utmp/vtmp (d2a2c_vect.py:19-65) on the full domain; zero delpc/ptc (c_sw.py:19-27)
+  // K1: utmp/vtmp (d2a2c_vect.py:19-65) on the full domain; zero delpc/ptc (c_sw.py:19-27) outside the transport's domain
   fv3::launch3d(ctx, st, 0, ied + 1, 0, jed + 1, 0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     const bool W = fv3::on_west(g, s), E = fv3::on_east(g, s), S = fv3::on_south(g, s), N = fv3::on_north(g, s);
     const int64_t o = O3(s, i, j, k);
-    delpc[o] = 0.0;
-    ptc[o] = 0.0;
+    if (i < isc - 1 || i > iec + 1 || j < jsc - 1 || j > jec + 1) {  // elsewhere the transport launch stores them
+      delpc[o] = 0.0;
+      ptc[o] = 0.0;
+    }
     const bool avg = (S && j < jsc + off) || (N && j > jec - off) || (W && i < isc + off) || (E && i > iec - off);
     double ut_ = BIG, vt_ = BIG;
     if (avg) {
@@ -125,8 +128,8 @@ int fv3_c_sw(fv3_ctx *ctx, double *delp, double *pt, const double *u, const doub
     }
   });
 
-  // K3: C-grid winds uc, vc and geo-adjusted contravariant fluxes ut, vt
-  // (d2a2c_vect.py:91-228, c_sw.py:156-199)
+  // K3 + K4: C-grid winds (into uc0, vc0: the wind update below reads them while it stores uc, vc) and geo-adjusted
+  // contravariant fluxes ut, vt (d2a2c_vect.py:91-228, c_sw.py:156-199); divergence at cell corners
   fv3::launch3d(ctx, st, isc - 1, iec + 3, jsc - 1, jec + 3, 0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     const bool W = fv3::on_west(g, s), E = fv3::on_east(g, s), S = fv3::on_south(g, s), N = fv3::on_north(g, s);
     const int64_t o = O3(s, i, j, k), o2 = O2(s, i, j);
@@ -150,7 +153,7 @@ int fv3_c_sw(fv3_ctx *ctx, double *delp, double *pt, const double *u, const doub
           ucv = A2 * (utmp[o - 2] + utmp[o + 1]) + A1 * (utmp[o - 1] + utmp[o]);
         utv = contravariant(ucv, v[o], m.cosa_u[o2], m.rsin_u[o2]);
       }
-      uc[o] = ucv;
+      uc0[o] = ucv;
       ut[o] = utv > 0 ? dt2 * utv * m.dy[o2] * m.sin_sg3[o2 - 1] : dt2 * utv * m.dy[o2] * m.sin_sg1[o2];
     }
     if (i <= iec + 1) {
@@ -173,15 +176,11 @@ int fv3_c_sw(fv3_ctx *ctx, double *delp, double *pt, const double *u, const doub
           vcv = A2 * (vtmp[o - 2 * sj] + vtmp[o + sj]) + A1 * (vtmp[o - sj] + vtmp[o]);
         vtv = contravariant(vcv, u[o], m.cosa_v[o2], m.rsin_v[o2]);
       }
-      vc[o] = vcv;
+      vc0[o] = vcv;
       vt[o] = vtv > 0 ? dt2 * vtv * m.dx[o2] * m.sin_sg4[o2 - sj] : dt2 * vtv * m.dx[o2] * m.sin_sg2[o2];
     }
-  });
-
-  // K4: divergence at cell corners (c_sw.py:31-154)
-  if (nord > 0) {
-    fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, 0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
-      const bool W = fv3::on_west(g, s), E = fv3::on_east(g, s), S = fv3::on_south(g, s), N = fv3::on_north(g, s);
+    // divergence at cell corners (c_sw.py:31-154): reads u, v, ua, va like the winds above, nothing the launch writes
+    if (nord > 0 && i >= isc && i <= iec + 1 && j >= jsc && j <= jec + 1) {
       auto uf = [&](int ii, int jj) {
         const int64_t o = O3(s, ii, jj, k), o2 = O2(s, ii, jj);
         if ((S && jj == jsc) || (N && jj == jec + 1)) return u[o] * m.dyc[o2] * 0.5 * (m.sin_sg4[o2 - sj] + m.sin_sg2[o2]);
@@ -204,8 +203,8 @@ int fv3_c_sw(fv3_ctx *ctx, double *delp, double *pt, const double *u, const doub
       else
         d = (vf(i, j - 1) - vf(i, j) + uf(i - 1, j) - uf(i, j)) * rc;
       divgd[O3(s, i, j, k)] = d;
-    });
-  }
+    }
+  });
 
   // K5 + K6: first-order upwind transport of delp, pt, w (c_sw.py:229-345), upstream kinetic energy and vorticity
   // (:347-364).  The x fluxes of a cell's two faces are formed on the fly (two multiplies each) instead of going through
@@ -262,8 +261,8 @@ int fv3_c_sw(fv3_ctx *ctx, double *delp, double *pt, const double *u, const doub
     ptc[o] = (pt0 * dp0 + (fxa - fxb + fya - fyb) * ra) / dpc;
     omga[o] = (w0 * dp0 + (fx2a - fx2b + fy2a - fy2b) * ra) / dpc;
     const double uav = ua[o], vav = va[o];
-    double kev = uav > 0.0 ? uc[o] : uc[o + 1];
-    double vo = vav > 0.0 ? vc[o] : vc[o + sj];
+    double kev = uav > 0.0 ? uc0[o] : uc0[o + 1];
+    double vo = vav > 0.0 ? vc0[o] : vc0[o + sj];
     if ((S && j == jsc - 1) || (N && j == jec)) vo = vav <= 0.0 ? vo * m.sin_sg4[o2] + u[o + sj] * m.cos_sg4[o2] : vo;
     if ((S && j == jsc) || (N && j == jec + 1)) vo = vav > 0.0 ? vo * m.sin_sg2[o2] + u[o] * m.cos_sg2[o2] : vo;
     if ((E && i == iec) || (W && i == isc - 1)) kev = uav <= 0.0 ? kev * m.sin_sg3[o2] + v[o + 1] * m.cos_sg3[o2] : kev;
@@ -288,34 +287,42 @@ int fv3_c_sw(fv3_ctx *ctx, double *delp, double *pt, const double *u, const doub
       q[O3(s, ic + xs, jc, k)] = q[O3(s, ic, jc - 2 * ys, k)];
   });
 
-  // K7: absolute vorticity at cell corners (c_sw.py:367-408)
-  fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, 0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
+  // K7 + K8: absolute vorticity at cell corners (c_sw.py:367-408) and the C-grid wind update (:411-480) in one launch.
+  // A wind needs the vorticity of ONE of two corners (the upwind one): it is evaluated on the fly from uc0 / vc0 instead
+  // of going through a field; the launch covers the whole domain the d2a2c winds were formed on and copies them where
+  // no update applies.
+  fv3::launch3d(ctx, st, isc - 1, iec + 3, jsc - 1, jec + 3, 0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
     const bool W = fv3::on_west(g, s), E = fv3::on_east(g, s), S = fv3::on_south(g, s), N = fv3::on_north(g, s);
     const int64_t o = O3(s, i, j, k), o2 = O2(s, i, j);
-    const double fxv = m.dxc[o2] * uc[o], fyv = m.dyc[o2] * vc[o];
-    const double fx1v = m.dxc[o2 - sj] * uc[o - sj], fy1v = m.dyc[o2 - 1] * vc[o - 1];
-    double vc_ = fx1v - fxv - fy1v + fyv;
-    const bool cj = (S && j == jsc) || (N && j == jec + 1);
-    if (W && i == isc && cj) vc_ = fx1v - fxv + fyv;
-    if (E && i == iec + 1 && cj) vc_ = fx1v - fxv - fy1v;
-    vort[o] = m.fC[o2] + m.rarea_c[o2] * vc_;
-  });
-
-  // K8: C-grid wind update (c_sw.py:411-480)
-  fv3::launch3d(ctx, st, isc, iec + 2, jsc, jec + 2, 0, nz, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
-    const bool W = fv3::on_west(g, s), E = fv3::on_east(g, s), S = fv3::on_south(g, s), N = fv3::on_north(g, s);
-    const int64_t o = O3(s, i, j, k), o2 = O2(s, i, j);
-    if (i <= iec) {
-      double tmp = dt2 * (u[o] - vc[o] * m.cosa_v[o2]) / m.sina_v[o2];
-      if ((S && j == jsc) || (N && j == jec + 1)) tmp = dt2 * u[o];
-      const double flux = tmp > 0.0 ? vort[o] : vort[o + 1];
-      vc[o] = vc[o] - tmp * flux + m.rdyc[o2] * (ke[o - sj] - ke[o]);
+    auto vort = [&](int ii, int jj) {
+      const int64_t oo = O3(s, ii, jj, k), oo2 = O2(s, ii, jj);
+      const double fxv = m.dxc[oo2] * uc0[oo], fyv = m.dyc[oo2] * vc0[oo];
+      const double fx1v = m.dxc[oo2 - sj] * uc0[oo - sj], fy1v = m.dyc[oo2 - 1] * vc0[oo - 1];
+      double vc_ = fx1v - fxv - fy1v + fyv;
+      const bool cj = (S && jj == jsc) || (N && jj == jec + 1);
+      if (W && ii == isc && cj) vc_ = fx1v - fxv + fyv;
+      if (E && ii == iec + 1 && cj) vc_ = fx1v - fxv - fy1v;
+      return m.fC[oo2] + m.rarea_c[oo2] * vc_;
+    };
+    if (i <= iec + 1) {
+      double vcv = vc0[o];
+      if (i >= isc && i <= iec && j >= jsc && j <= jec + 1) {
+        double tmp = dt2 * (u[o] - vcv * m.cosa_v[o2]) / m.sina_v[o2];
+        if ((S && j == jsc) || (N && j == jec + 1)) tmp = dt2 * u[o];
+        const double flux = vort(tmp > 0.0 ? i : i + 1, j);
+        vcv = vcv - tmp * flux + m.rdyc[o2] * (ke[o - sj] - ke[o]);
+      }
+      vc[o] = vcv;
     }
-    if (j <= jec) {
-      double tmp = dt2 * (v[o] - uc[o] * m.cosa_u[o2]) / m.sina_u[o2];
-      if ((W && i == isc) || (E && i == iec + 1)) tmp = dt2 * v[o];
-      const double flux = tmp > 0.0 ? vort[o] : vort[o + sj];
-      uc[o] = uc[o] + tmp * flux + m.rdxc[o2] * (ke[o - 1] - ke[o]);
+    if (j <= jec + 1) {
+      double ucv = uc0[o];
+      if (i >= isc && i <= iec + 1 && j >= jsc && j <= jec) {
+        double tmp = dt2 * (v[o] - ucv * m.cosa_u[o2]) / m.sina_u[o2];
+        if ((W && i == isc) || (E && i == iec + 1)) tmp = dt2 * v[o];
+        const double flux = vort(i, tmp > 0.0 ? j : j + 1);
+        ucv = ucv + tmp * flux + m.rdxc[o2] * (ke[o - 1] - ke[o]);
+      }
+      uc[o] = ucv;
     }
   });
   return fv3::check_launch("fv3_c_sw");

@@ -27,7 +27,9 @@ struct PlaneArgs {
 
 // NC: the final-flux operands xu / yu are read-only for the whole kernel (read through the non-coherent path); false
 // when the same kernel wrote them earlier (the fused d_sw stage keeps its mass fluxes in a scratch field).
-template <int MORD, bool NC = true>
+// PRELOADED: the caller has already issued the bulk copy of q's resident rows into Q (it overlaps the caller's previous
+// phase); only the wait for it happens here.
+template <int MORD, bool NC = true, bool PRELOADED = false>
 FV_DEV void fvtp2d_plane(const fv3_geom &g, const fv3_grid &m, int s, int k, const Block &b, const PlaneArgs &a,
                         double *Q, double *A, double *B, double *D, double *T) {
   const int sj = g.sj, h = g.halo, nx = g.nx, ny = g.ny;
@@ -51,8 +53,10 @@ FV_DEV void fvtp2d_plane(const fv3_geom &g, const fv3_grid &m, int s, int k, con
   }
   // 1. load q: the strip's resident rows are one contiguous range of the global plane -> ONE bulk (TMA) copy; then the
   //    3x3 cube-corner halo blocks as copy_corners_y leaves them
-  b.bulk_begin(1, sj);
-  b.bulk_rows(Q, q, sj);
+  if (!PRELOADED) {
+    b.bulk_begin(1, sj);
+    b.bulk_rows(Q, q, sj);
+  }
   b.bulk_wait();
   if (a.add2d) b.rect(0, nwi, rl, rh, [&](int i, int j) { Q[j * sj + i] = Q[j * sj + i] + a.add2d[j * sj + i]; });
   // the cube-corner halo blocks need their copy_corners_y / copy_corners_x forms only on tile-corner subdomains, and

@@ -2,16 +2,39 @@
 //   fv3_update_dz_d <- UpdateHeightOnDGrid.__call__ (fv3core/pace/fv3core/stencils/updatedzd.py:283-356)
 #include "common.h"
 #include "fdiv.h"
-
-extern "C" int fv3_fvtp2d(fv3_ctx *, const double *, const double *, const double *, const double *, const double *,
-                          double *, double *, const double *, const double *, const double *, int, const double *,
-                          const double *, int, int, void *);
-extern "C" int fv3_delnflux_nosg(fv3_ctx *, const double *, double *, double *, const double *, const double *, int,
-                                 int, void *);
+#include "transport.h"
 
 namespace {
 constexpr double DZ_MIN = 2.0;
 constexpr int NKMAX = 96;
+
+// Transport of the interface heights with the interpolated Courant numbers / area fluxes (updatedzd.py:331-343), the
+// del-n damping fluxes of the heights (DelnFluxNoSG, :344-345) and the flux-form update of apply_height_fluxes
+// (:70-106) as ONE strip-resident kernel: the four flux fields stay in shared memory (B, A: transport; D, T: damping)
+// and are applied in the CTA that produced them.  The heights are only read here (the update goes to `hraw`), so no
+// row needs parking.
+template <int MORD>
+int height_fluxes_launch(const fv3_ctx *ctx, cudaStream_t st, const double *height, const double *crx_i, const double *cry_i,
+                         const double *xfx_i, const double *yfx_i, double *hraw, const double *damp_col,
+                         const double *nord_col, int nmax) {
+  const fv3_geom g = ctx->g;
+  const fv3_grid m = ctx->m;
+  return fv3::launch_planes(ctx, st, 0, g.nz + 1, fv3::FVTP_PLANES, FV_LAMBDA(int s, int k, const fv3::Block &b) { FV_DEV_GM
+    double *Q = b.plane(0), *A = b.plane(1), *B = b.plane(2), *D = b.plane(3), *T = b.plane(4);
+    const int sj = g.sj, h = g.halo, nx = g.nx;
+    const int64_t ob = O3(s, 0, 0, k), o2b = O2(s, 0, 0);
+    const fv3::PlaneArgs pa{height, crx_i, cry_i, xfx_i, yfx_i, xfx_i, yfx_i};
+    fv3::fvtp2d_plane<MORD>(g, m, s, k, b, pa, Q, A, B, D, T);
+    fv3::delnflux_plane(g, m, s, b, height + ob, damp_col[k], nord_col[k] > 0, nmax, false, Q, D, T);
+    const double *area = m.area + o2b, *xf = xfx_i + ob, *yf = yfx_i + ob, *hg = height + ob;
+    b.rect(h, h + nx, b.ja, b.jb, [&](int i, int j) {
+      const int p = j * sj + i;
+      const double ar = FV_LDG(area + p);
+      const double area_after = ((ar + FV_LDG(xf + p) - FV_LDG(xf + p + 1)) + (ar + FV_LDG(yf + p) - FV_LDG(yf + p + sj))) - ar;
+      hraw[ob + p] = (FV_LDG(hg + p) * ar + B[p] - B[p + 1] + A[p] - A[p + sj]) / area_after + (D[p] - D[p + 1] + T[p] - T[p + sj]) / ar;
+    });
+  });
+}
 }  // namespace
 
 extern "C" {
@@ -30,8 +53,6 @@ int fv3_update_dz_d(fv3_ctx *ctx, const double *surface_height, double *height, 
   }
   double *crx_i = fv3::scratch_field(ctx, 16), *cry_i = fv3::scratch_field(ctx, 17);
   double *xfx_i = fv3::scratch_field(ctx, 18), *yfx_i = fv3::scratch_field(ctx, 19);
-  double *fx = fv3::scratch_field(ctx, 20), *fy = fv3::scratch_field(ctx, 21);
-  double *gx = fv3::scratch_field(ctx, 22), *gy = fv3::scratch_field(ctx, 23);
   // cubic_spline_interpolation_from_layer_center_to_interfaces (updatedzd.py:157-196), 4 fields, full domain.
   // One thread per column and field, partial solution in thread-local memory: at 472 K independent columns the
   // full-occupancy form beats shared-memory chains (measured: 384 us against 590 us, profiles/).
@@ -93,21 +114,23 @@ int fv3_update_dz_d(fv3_ctx *ctx, const double *surface_height, double *height, 
       qi[c0 + kb * sk] = above;
     }
   });
-  int rc;
-  if ((rc = fv3_fvtp2d(ctx, height, crx_i, cry_i, xfx_i, yfx_i, fx, fy, nullptr, nullptr, nullptr, ctx->c.hord_tm, nullptr,
-                       nullptr, 0, nz + 1, stream)))
-    return rc;
-  if ((rc = fv3_delnflux_nosg(ctx, height, gx, gy, damp_col, nord_col, nmax, nz + 1, stream))) return rc;
-  // apply_height_fluxes (updatedzd.py:70-126): compute domain.  The flux-form update of every level is independent and
-  // runs level-parallel (into a scratch field); only the BACKWARD
-  // monotonicity fix is a column walk, with its loads fetched 8 levels ahead of the dependent max-chain.
+  // transport + del-n damping + apply_height_fluxes (updatedzd.py:70-126, 331-345), compute domain, one launch.  The
+  // flux-form update of every level is independent (into a scratch field); only the BACKWARD monotonicity fix is a column
+  // walk, with its loads fetched 8 levels ahead of the dependent max-chain.
+  if (nmax > 2 || nmax < 0) {
+    fv3::set_error("fv3_update_dz_d: nmax must be 0..2 (halo 3)");
+    return -1;
+  }
   double *hraw = fv3::scratch_field(ctx, 24);
-  fv3::launch3d(ctx, st, isc, iec + 1, jsc, jec + 1, 0, nz + 1, FV_LAMBDA(int s, int i, int j, int k) { FV_DEV_GM
-    const int64_t o = O3(s, i, j, k);
-    const double ar = m.area[O2(s, i, j)];
-    const double area_after = ((ar + xfx_i[o] - xfx_i[o + 1]) + (ar + yfx_i[o] - yfx_i[o + sj])) - ar;
-    hraw[o] = (height[o] * ar + fx[o] - fx[o + 1] + fy[o] - fy[o + sj]) / area_after + (gx[o] - gx[o + 1] + gy[o] - gy[o + sj]) / ar;
-  });
+  const int mord = ctx->c.hord_tm < 0 ? -ctx->c.hord_tm : ctx->c.hord_tm;
+  int rc;
+  if (mord == 8 || mord == 10)
+    rc = height_fluxes_launch<8>(ctx, st, height, crx_i, cry_i, xfx_i, yfx_i, hraw, damp_col, nord_col, nmax);
+  else if (mord == 5)
+    rc = height_fluxes_launch<5>(ctx, st, height, crx_i, cry_i, xfx_i, yfx_i, hraw, damp_col, nord_col, nmax);
+  else
+    rc = height_fluxes_launch<6>(ctx, st, height, crx_i, cry_i, xfx_i, yfx_i, hraw, damp_col, nord_col, nmax);
+  if (rc) return rc;
   fv3::launch2d(ctx, st, isc, iec + 1, jsc, jec + 1, FV_LAMBDA(int s, int i, int j) { FV_DEV_GM
     const int64_t c0 = O3(s, i, j, 0), sk = g.sk;
     double below = hraw[c0 + nz * sk];
