@@ -21,7 +21,15 @@
 namespace fv3 {
 
 constexpr int COL_TILE = 32;
-constexpr int COL_WARPS = 16;
+// Warps per tile and tiles per SM (measured on the Riemann solvers, whose three [level][column] arrays take 61 KB per tile:
+// 2 x 16 warps 850 us, 3 x 14 760 us, 3 x 12 705 us, 3 x 10 775 us, 3 x 8 810 us per call at C128)
+#ifndef FV3_COL_WARPS
+#define FV3_COL_WARPS 12
+#endif
+#ifndef FV3_COL_MINB
+#define FV3_COL_MINB 3
+#endif
+constexpr int COL_WARPS = FV3_COL_WARPS;
 
 struct Tile {
   double *sm;       // n_arrays * nlev * COL_TILE doubles
@@ -70,7 +78,7 @@ struct Tile {
 
 #ifndef FV3_HOSTSIM
 template <class F>
-__global__ void __launch_bounds__(COL_TILE *COL_WARPS) kcolumns(F f, int i0, int ni, int j0, int ncols, int nlev) {
+__global__ void __launch_bounds__(COL_TILE *COL_WARPS, FV3_COL_MINB) kcolumns(F f, int i0, int ni, int j0, int ncols, int nlev) {
   extern __shared__ double col_smem[];
   Tile t;
   t.sm = col_smem;

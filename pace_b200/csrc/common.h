@@ -71,9 +71,12 @@ FV_HD bool on_north(const fv3_geom &g, int s) { return g.edge[s] & FV3_EDGE_NORT
 FV_HD double dmin(double a, double b) { return a < b ? a : b; }
 FV_HD double dmax(double a, double b) { return a > b ? a : b; }
 
+#ifndef FV3_K3D_THREADS
+#define FV3_K3D_THREADS 128
+#endif
 #ifndef FV3_HOSTSIM
 template <class F>
-__global__ void __launch_bounds__(128) k3d(F f, int i0, int ni, int j0, int nj, int k0) {
+__global__ void __launch_bounds__(FV3_K3D_THREADS) k3d(F f, int i0, int ni, int j0, int nj, int k0) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= ni * nj) return;
   int j = idx / ni;
@@ -122,8 +125,8 @@ inline void launch3d(const fv3_ctx *ctx, cudaStream_t st, int i0, int i1, int j0
         for (int i = i0; i < i1; ++i) f(s, i, j, k);
 #else
   activate(ctx, st);
-  dim3 grid((ni * nj + 127) / 128, nk, ctx->g.n_sub);
-  k3d<<<grid, 128, 0, st>>>(f, i0, ni, j0, nj, k0);
+  dim3 grid((ni * nj + FV3_K3D_THREADS - 1) / FV3_K3D_THREADS, nk, ctx->g.n_sub);
+  k3d<<<grid, FV3_K3D_THREADS, 0, st>>>(f, i0, ni, j0, nj, k0);
   ++g_launches;
 #endif
 }

@@ -618,7 +618,7 @@ void unpark_rows(const fv3_ctx *ctx, cudaStream_t st, Fields4 fl, int nf, double
 // The eight steps run as ONE loop around a single transport body and a single del-n body (a step table selects the
 // field and the operands), so that the kernel holds one copy of each sweep instead of four.
 // MDP / MVT / MTM: |hord_dp|, |hord_vt|, |hord_tm| (5, 6 or 8).
-template <int MDP, int MVT, int MTM>
+template <int MDP, int MVT, int MTM, int PARTS = 15>
 int dsw_scalars_launch(fv3_ctx *ctx, cudaStream_t st, double *delp, double *pt, double *w, double *q_con, const double *crx,
                        const double *cry, const double *xfx, const double *yfx, double *mfx, double *mfy, double *heat_s,
                        double *diss_est, double *fxs, double *fys, double *side0, double dt, const fv3_dsw_cols *c,
@@ -665,6 +665,7 @@ int dsw_scalars_launch(fv3_ctx *ctx, cudaStream_t st, double *delp, double *pt, 
     typedef std::integral_constant<int, same ? MTM : 0> TagTM;
     // (1) mass: delp transport + del-n damping (d_sw.py:967-975); mass fluxes kept for the other transports and
     //     accumulated (flux_capacitor)
+    if (PARTS & 1) {
     transport(TagDP(), delp, xfx, yfx);
     fv3::delnflux_plane(g, m, s, b, dp, cl.dn_damp_vt[k], cl.nord_v[k] > 0, cl.nmax_v, false, Q, D, T);
     b.rect(isc, iec + 2, ja, jb + 1, [&](int i, int j) {
@@ -680,6 +681,8 @@ int dsw_scalars_launch(fv3_ctx *ctx, cudaStream_t st, double *delp, double *pt, 
         if (j <= jt) mfy[ob + p] = mfy[ob + p] + fl;
       }
     });
+    }
+    if (PARTS & 2) {
     // (2) w: del-n fluxes of damp_w * w and the heat they dissipate (d_sw.py:53-103); dw goes to T for the update
     fv3::delnflux_plane(g, m, s, b, w + ob, cl.dn_damp_w_c[k], cl.nord_w[k] > 0, cl.nmax_w, false, Q, A, B);
     {
@@ -707,6 +710,7 @@ int dsw_scalars_launch(fv3_ctx *ctx, cudaStream_t st, double *delp, double *pt, 
       if (damp_w > 1e-5) wv = wv + T[p];
       (parked(j) ? side0 : w)[o] = wv;
     });
+    }
     // (4) q_con and (5) pt: transport, mass-weighted del-n damping (delnflux.py:1164-1207, 215-238), update
     auto damped_update = [&](double *q, double dk, bool hi, int nmax, double *side) {
       fv3::delnflux_plane(g, m, s, b, q + ob, dk, hi, nmax, true, Q, D, T);
@@ -724,12 +728,16 @@ int dsw_scalars_launch(fv3_ctx *ctx, cudaStream_t st, double *delp, double *pt, 
         (parked(j) ? side : q)[o] = qv;
       });
     };
-    transport(TagDP(), q_con, fxs, fys);
-    damped_update(q_con, cl.dn_damp_t[k], cl.nord_t[k] > 0, cl.nmax_t, side0 + side_stride);
-    transport(TagTM(), pt, fxs, fys);
-    damped_update(pt, cl.dn_damp_vt[k], cl.nord_v[k] > 0, cl.nmax_v, side0 + 2 * side_stride);
+    if (PARTS & 4) {
+      transport(TagDP(), q_con, fxs, fys);
+      damped_update(q_con, cl.dn_damp_t[k], cl.nord_t[k] > 0, cl.nmax_t, side0 + side_stride);
+    }
+    if (PARTS & 8) {
+      transport(TagTM(), pt, fxs, fys);
+      damped_update(pt, cl.dn_damp_vt[k], cl.nord_v[k] > 0, cl.nmax_v, side0 + 2 * side_stride);
+    }
     // the new mass itself
-    {
+    if (PARTS & 8) {
       double *side = side0 + 3 * side_stride;
       b.rect(isc, iec + 1, ja, jb, [&](int i, int j) {
         const int p = j * sj + i;
@@ -791,8 +799,18 @@ int fv3_d_sw(fv3_ctx *ctx, double *delpc, double *delp, double *pt, double *u, d
   {
     auto mo = [](int hord) { const int a = hord < 0 ? -hord : hord; return a == 10 ? 8 : a; };
     const int mdp = mo(cfg.hord_dp), mvt = mo(cfg.hord_vt), mtm = mo(cfg.hord_tm);
-#define DSW_SCALARS(A_, B_, C_) \
-  dsw_scalars_launch<A_, B_, C_>(ctx, st, delp, pt, w, q_con, crx, cry, xfx, yfx, mfx, mfy, heat_s, diss_est, fx, fy, side0, dt, c, mdp, mvt, mtm)
+#ifndef FV3_K2_SPLIT
+#define FV3_K2_SPLIT 4
+#endif
+#define DSW_PART(A_, B_, C_, P_) \
+  dsw_scalars_launch<A_, B_, C_, P_>(ctx, st, delp, pt, w, q_con, crx, cry, xfx, yfx, mfx, mfy, heat_s, diss_est, fx, fy, side0, dt, c, mdp, mvt, mtm)
+#if FV3_K2_SPLIT == 4
+#define DSW_SCALARS(A_, B_, C_) ((rc = DSW_PART(A_, B_, C_, 1)) || (rc = DSW_PART(A_, B_, C_, 2)) || (rc = DSW_PART(A_, B_, C_, 4)) || (rc = DSW_PART(A_, B_, C_, 8)), rc)
+#elif FV3_K2_SPLIT == 2
+#define DSW_SCALARS(A_, B_, C_) ((rc = DSW_PART(A_, B_, C_, 3)) || (rc = DSW_PART(A_, B_, C_, 12)), rc)
+#else
+#define DSW_SCALARS(A_, B_, C_) DSW_PART(A_, B_, C_, 15)
+#endif
     if (mdp == 6 && mvt == 6 && mtm == 6)
       rc = DSW_SCALARS(6, 6, 6);
     else if (mdp == 5 && mvt == 5 && mtm == 5)
@@ -802,6 +820,7 @@ int fv3_d_sw(fv3_ctx *ctx, double *delpc, double *delp, double *pt, double *u, d
     else
       rc = DSW_SCALARS(0, 1, 2);  // mixed orders: one kernel with all three sweep bodies, selected per field
 #undef DSW_SCALARS
+#undef DSW_PART
     if (rc) return rc;
   }
   unpark_rows(ctx, st, Fields4{{w, q_con, pt, delp}}, 4, side0, nz);

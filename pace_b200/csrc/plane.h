@@ -25,7 +25,10 @@ constexpr int PLANE_THREADS = 512;
 // guard doubles before the first / after the last shared plane: the register-window loads of the PPM sweeps (sweep.h)
 // run unconditionally and may reach 4 doubles before a row and 2 rows beyond the resident range (never used, never stored)
 constexpr int PLANE_PAD_FRONT = 16;
-FV_HD int plane_pad_back(int sj) { return 2 * sj + 16; }
+#ifndef FV3_SWEEP_R
+#define FV3_SWEEP_R 4
+#endif
+FV_HD int plane_pad_back(int sj) { return (FV3_SWEEP_R > 4 ? FV3_SWEEP_R - 2 : 2) * sj + 16; }
 constexpr int PLANE_SMEM_BUDGET = (233472 / 2) - 1024;  // bytes per CTA for two CTAs per SM (228 KB, 1 KB reserved each)
 
 // t / w for the index decode of a block-wide pass without an integer division (20+ instructions per point): exact for

@@ -14,7 +14,10 @@
 
 namespace fv3 {
 
-constexpr int SWEEP_R = 4;  // faces per task
+#ifndef FV3_SWEEP_R
+#define FV3_SWEEP_R 4
+#endif
+constexpr int SWEEP_R = FV3_SWEEP_R;  // faces per task (even: the x-sweep windows are read as aligned pairs)
 
 #ifdef FV3_HOSTSIM
 FV_HD void ld_pair(const double *p, double &a, double &b) {
@@ -116,7 +119,7 @@ struct Sweep {
     const bool any = nl > 0 && f1 >= f0;
     nfv = fv1 >= fv0 ? (unsigned)(fv1 - fv0) : 0u;
     // x sweeps: groups start at multiples of R so that the 128-bit window loads are aligned
-    fb = XDIR ? (fv0 & ~(R - 1)) : fv0;
+    fb = XDIR ? ((R & (R - 1)) == 0 ? (fv0 & ~(R - 1)) : (fv0 & ~1)) : fv0;
     ng = (any && fv1 >= fv0) ? (fv1 - fb) / R + 1 : 0;
     nbulk = ng * nl;
     n = any ? nbulk + ((e.lo || e.hi) ? 2 * nl : 0) : 0;
