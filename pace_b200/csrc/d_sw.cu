@@ -8,6 +8,10 @@
 #include "a2b.h"
 #include "transport.h"
 
+#ifndef FV3_K3B_LOOP
+#define FV3_K3B_LOOP true
+#endif
+
 namespace fv3 {
 int fv_prep_launch(fv3_ctx *ctx, cudaStream_t st, const double *uc, const double *vc, double *crx, double *cry, double *xfx,
                    double *yfx, double *ucc_out, double *vcc_out, double *cx, double *cy, double dt, bool store_all);
@@ -537,7 +541,7 @@ int dsw_winds_launch(fv3_ctx *ctx, cudaStream_t st, double *u, double *v, const 
     // absolute vorticity = relative vorticity + f0, transported with the area fluxes (d_sw.py:1131-1147)
     fv3::PlaneArgs pa{vort_a, crx, cry, xfx, yfx, xfx, yfx};
     pa.add2d = m.f0 + o2b;
-    fv3::fvtp2d_plane<MORD, true>(g, m, s, k, b, pa, Q, A, B, D, T);
+    fv3::fvtp2d_plane<MORD, true, false, FV3_K3B_LOOP>(g, m, s, k, b, pa, Q, A, B, D, T);
     // u_and_v_from_ke (d_sw.py:439-477): u' -> Q on faces [ja, jb], v' -> D on rows [ja, jb)
     {
       const double *kp = ke + ob, *up = u + ob, *vp = v + ob;
@@ -647,16 +651,16 @@ int dsw_scalars_launch(fv3_ctx *ctx, cudaStream_t st, double *delp, double *pt, 
       constexpr int MO = decltype(mord_tag)::value;
       const fv3::PlaneArgs pa{q, crx, cry, xfx, yfx, xu, yu};
       if (MO != 0) {
-        fv3::fvtp2d_plane<MO == 0 ? 6 : MO, false>(g, m, s, k, b, pa, Q, A, B, D, T);
+        fv3::fvtp2d_plane<MO == 0 ? 6 : MO, false, false, true>(g, m, s, k, b, pa, Q, A, B, D, T);
       } else {
         // mixed orders: the true |hord| of this field is a run-time value
         const int mord = q == w ? rvt : (q == pt ? rtm : rdp);
         if (mord == 8)
-          fv3::fvtp2d_plane<8, false>(g, m, s, k, b, pa, Q, A, B, D, T);
+          fv3::fvtp2d_plane<8, false, false, true>(g, m, s, k, b, pa, Q, A, B, D, T);
         else if (mord == 5)
-          fv3::fvtp2d_plane<5, false>(g, m, s, k, b, pa, Q, A, B, D, T);
+          fv3::fvtp2d_plane<5, false, false, true>(g, m, s, k, b, pa, Q, A, B, D, T);
         else
-          fv3::fvtp2d_plane<6, false>(g, m, s, k, b, pa, Q, A, B, D, T);
+          fv3::fvtp2d_plane<6, false, false, true>(g, m, s, k, b, pa, Q, A, B, D, T);
       }
     };
     constexpr bool same = MDP == MVT && MDP == MTM;
