@@ -44,9 +44,8 @@ int fv3_nh_p_grad(fv3_ctx *ctx, double *u, double *v, double *pp, double *gz, do
     field(0, src, dst);
     b.bulk_begin(1, sj2);
     b.bulk_rows(SQ0, src + ob, sj2);
-#pragma unroll
-    for (int f = 0; f < 4; ++f) {
-      if (f >= nf) break;
+#pragma unroll 1
+    for (int f = 0; f < nf; ++f) {
       double *SQ = (f & 1) ? SQ1 : SQ0;
       field(f, src, dst);
       b.bulk_wait();
