@@ -105,6 +105,15 @@ int64_t fv3_launch_count(void);
 /* measurement aid: blocks x 128 threads run iters x 8 independent fp64 FMAs each (2 * 8 * iters * 128 * blocks flops);
  * out: blocks * 128 doubles.  bench.py times it to get the fp64 roof of this GPU. */
 int fv3_fp64_peak(double *out, int iters, int blocks, void *stream);
+/* ---- optional state sanity check: replaces the min / max / NaN scans of SafetyChecker.check_state
+ *      (driver/pace/driver/safety_checks.py:70-110) and the negative-delp / negative-tracer / NaN checks of the DaCe
+ *      debug passes (dsl/pace/dsl/dace/sdfg_debug_passes.py:185-269) by one pass over the field.
+ * out (device, 3 x int64): key of the minimum and of the maximum over the non-NaN values — key = bits ^ ((bits >> 63) &
+ * 0x7fffffffffffffff), an order-preserving involution of the fp64 bit pattern — and the number of NaN values, over the
+ * points i in [i0, i1), j in [j0, j1), levels [0, nk) of every local subdomain (a Quantity's view or its whole storage);
+ * nk == 0: 2-D field. */
+int fv3_field_check(fv3_ctx *ctx, const double *field, int i0, int i1, int j0, int j1, int nk, int64_t *out,
+                    void *stream);
 /* number of 3-D scratch fields fv3_create needs (scratch_bytes >= n * ss * n_sub * 8) */
 int fv3_scratch_fields(void);
 
