@@ -453,6 +453,8 @@ def main():
         "metric": "C128L79 baroclinic dycore s/timestep", "value": ms / 1e3, "unit": "s/timestep", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args), "clocks": clocks,
+        "halo_transport": ("device-local gathers only" if world == 1 else
+                           ("fv3_halo_exchange_nccl (C ABI, own ncclComm_t)" if pc.nccl_comm is not None else "torch.distributed.batch_isend_irecv")),
         "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "fp64_peak_tflops": fp64_peak, "finite": finite,
         "state_digest": digest,
         "launch_mode": mode, "ms_per_step_eager": ms_eager, "host_enqueue_ms_per_step": host_enqueue_ms,

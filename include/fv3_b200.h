@@ -130,6 +130,19 @@ int fv3_halo_pack(const fv3_geom *geom, double *const *fields, int n_fields, int
                   const int8_t *src_comp, const double *sign, int64_t n_entries, double *buf, void *stream);
 int fv3_halo_unpack(const fv3_geom *geom, double *const *fields, int n_fields, int nlev, const int64_t *dst_off,
                     const int8_t *dst_comp, int64_t n_entries, const double *buf, void *stream);
+/* ---- inter-GPU messages of an exchange as one C call: replaces the Isend / Irecv pairs of
+ *      HaloUpdater.start (util/pace/util/halo_updater.py:217-303) by ONE grouped ncclSend / ncclRecv per peer GPU on the
+ *      packed segments below, asynchronous on `stream`.  NCCL is resolved at run time from the process's libnccl.so.2
+ *      (fv3_nccl_available() == 0 when there is none).  A communicator is created collectively from 128 id bytes that
+ *      rank 0 obtains and distributes (fv3_nccl_unique_id, fv3_nccl_comm_create); an integration that already owns an
+ *      ncclComm_t passes it straight in.  Offsets and counts are in doubles, host arrays. */
+int fv3_nccl_available(void);
+int fv3_nccl_unique_id(char *id128);
+int fv3_nccl_comm_create(void **comm, int nranks, const char *id128, int rank);
+int fv3_nccl_comm_destroy(void *comm);
+int fv3_halo_exchange_nccl(void *nccl_comm, const double *send_buf, const int64_t *send_off, const int64_t *send_cnt,
+                           const int32_t *send_peer, int n_send, double *recv_buf, const int64_t *recv_off,
+                           const int64_t *recv_cnt, const int32_t *recv_peer, int n_recv, void *stream);
 /* segmented forms: ONE launch per exchange for all peer GPUs.  buf holds one contiguous segment per peer (the NCCL
  * send / recv message, halo_updater.py:217-303 posts one Isend/Irecv per neighbour); entry e lives at
  *   buf[seg_base[e] + (f*nlev + k)*seg_n[e] + seg_e[e]].                                                   */

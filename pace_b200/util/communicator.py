@@ -14,6 +14,7 @@ Design: the gather table of pace_b200.util.topology is split by where source and
                    enqueues between start() and wait() overlaps the inter-GPU exchange.
 """
 import ctypes
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -64,12 +65,50 @@ class ProcessComm:
         self.rank = rank
         self.size = size
         self.group = group
+        self.nccl_comm = None   # ncclComm_t of the native exchange (fv3_halo_exchange_nccl); None: torch.distributed p2p
 
     @classmethod
-    def from_torch_distributed(cls, group=None):
+    def from_torch_distributed(cls, group=None, native_nccl=None):
+        """Process communicator over a torch.distributed group.  On an NCCL group the halo messages go through the C ABI
+        (`fv3_halo_exchange_nccl`, one grouped ncclSend / ncclRecv per exchange on a communicator of this library's own,
+        created here from a unique id broadcast over the group); `native_nccl=False` or FV3_NATIVE_NCCL=0 keeps
+        `torch.distributed.batch_isend_irecv`, as does any failure to set the native communicator up."""
         import torch.distributed as dist
 
-        return cls(dist.get_rank(group), dist.get_world_size(group), group)
+        pc = cls(dist.get_rank(group), dist.get_world_size(group), group)
+        if native_nccl is None:
+            native_nccl = os.environ.get("FV3_NATIVE_NCCL", "1") != "0"
+        if native_nccl and pc.size > 1 and dist.get_backend(group) == "nccl":
+            pc._create_nccl_comm()
+        return pc
+
+    def _create_nccl_comm(self):
+        import ctypes
+
+        import torch.distributed as dist
+
+        lib = _lib.load()
+        ok = torch.tensor([1 if lib.fv3_nccl_available() else 0], dtype=torch.int32, device="cuda")
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0 and int(ok.item()):
+            buf = ctypes.create_string_buffer(128)
+            if lib.fv3_nccl_unique_id(buf) == 0:
+                ident = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+            else:
+                ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)   # every rank takes the same decision
+        if not int(ok.item()):
+            return
+        ident = ident.cuda()
+        dist.broadcast(ident, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
+        handle = ctypes.c_void_p()
+        rc = lib.fv3_nccl_comm_create(ctypes.byref(handle), self.size, bytes(ident.cpu().numpy().tobytes()), self.rank)
+        good = torch.tensor([1 if rc == 0 and handle.value else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(good, op=dist.ReduceOp.MIN, group=self.group)
+        if int(good.item()):
+            self.nccl_comm = handle.value
+        elif rc == 0 and handle.value:
+            lib.fv3_nccl_comm_destroy(handle)
 
     def Get_rank(self):
         return self.rank
@@ -152,6 +191,7 @@ class HaloUpdater:
                 seg["d_seg_e"] = dev_t(seg["seg_e"], torch.int32)
                 seg["n"] = int(len(seg["off"]))
         self._bufs: Dict[int, tuple] = {}
+        self._nccl_cache: Dict[int, tuple] = {}
         self._ptr_cache: Dict[tuple, torch.Tensor] = {}
         self._pending = None
         _ = total
@@ -186,6 +226,30 @@ class HaloUpdater:
             self._bufs[n_fields] = b
         return b
 
+    def _nccl_args(self, n_fields, sb, rb):
+        """Host-side message table of fv3_halo_exchange_nccl for an exchange of n_fields fields (cached)."""
+        a = self._nccl_cache.get(n_fields)
+        if a is None:
+            per = n_fields * self._nlev
+
+            def side(seg, bufs):
+                if seg is None:
+                    return [None, None, None, None, 0]
+                cnt = np.array([n * per for _, n in seg["peers"]], dtype=np.int64)
+                off = np.concatenate([[0], np.cumsum(cnt)[:-1]]).astype(np.int64)
+                peer = np.array([p for p, _ in seg["peers"]], dtype=np.int32)
+                return [bufs[0].data_ptr(), off, cnt, peer, len(peer)]
+
+            s_, r_ = side(self._send, sb), side(self._recv, rb)
+            keep = (s_, r_)   # the numpy arrays must outlive the ctypes pointers taken from them
+
+            def ptr(x):
+                return None if x is None else x.ctypes.data
+
+            a = (s_[0], ptr(s_[1]), ptr(s_[2]), ptr(s_[3]), s_[4], r_[0], ptr(r_[1]), ptr(r_[2]), ptr(r_[3]), r_[4], keep)
+            self._nccl_cache[n_fields] = a
+        return a[:-1]
+
     def start(self, quantities_x: Sequence[Quantity], quantities_y: Optional[Sequence[Quantity]] = None):
         if self._inflight:
             raise RuntimeError("HaloUpdater.start called twice without a wait() in between")
@@ -216,11 +280,17 @@ class HaloUpdater:
                         gp, ptrs.data_ptr(), n_fields, self._nlev, S["d_off"].data_ptr(), S["d_comp"].data_ptr(),
                         S["d_sign"].data_ptr(), base.data_ptr(), S["d_seg_n"].data_ptr(), S["d_seg_e"].data_ptr(), S["n"],
                         buf.data_ptr(), cstream), "fv3_halo_pack_segments")
-                    ops += [dist.P2POp(dist.isend, v, peer, comm.process_comm.group) for (peer, _), v in zip(S["peers"], views)]
-                if self._recv is not None:
-                    ops += [dist.P2POp(dist.irecv, v, peer, comm.process_comm.group)
-                            for (peer, _), v in zip(self._recv["peers"], rb[1])]
-                reqs = dist.batch_isend_irecv(ops)
+                    if comm.process_comm.nccl_comm is None:
+                        ops += [dist.P2POp(dist.isend, v, peer, comm.process_comm.group) for (peer, _), v in zip(S["peers"], views)]
+                if comm.process_comm.nccl_comm is not None:
+                    # the messages of all peers: ONE C call, grouped ncclSend / ncclRecv on the communication stream
+                    msg = self._nccl_args(n_fields, sb, rb)
+                    _lib.check(lib, lib.fv3_halo_exchange_nccl(comm.process_comm.nccl_comm, *msg, cstream), "fv3_halo_exchange_nccl")
+                else:
+                    if self._recv is not None:
+                        ops += [dist.P2POp(dist.irecv, v, peer, comm.process_comm.group)
+                                for (peer, _), v in zip(self._recv["peers"], rb[1])]
+                    reqs = dist.batch_isend_irecv(ops)
         if self._n_local:
             L = self._loc
             _lib.check(lib, lib.fv3_halo_gather(gp, ptrs.data_ptr(), n_fields, self._nlev, L["dst_off"].data_ptr(),

@@ -1,5 +1,6 @@
 """One strict step case on SEVERAL GPUs (launched by torch.distributed.run, one process per GPU): the inter-GPU halo path
-(fv3_halo_pack_segments -> NCCL send/recv -> fv3_halo_unpack_segments on the communication stream) against the
+(fv3_halo_pack_segments -> fv3_halo_exchange_nccl, or torch.distributed send/recv with FV3_NATIVE_NCCL=0 ->
+fv3_halo_unpack_segments on the communication stream) against the
 reference's final state.  Every process checks the reference ranks it owns; exit code 0 = all within tolerance.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29531 \
@@ -43,8 +44,12 @@ def main():
     mine = {r: z for r, z in s1.items() if r in comm.local_ranks}
     failures, achieved = S.compare(out, mine, meta, first_rank=comm.first_rank)
     worst = max([v[0] for v in achieved.values()] + [0.0])
+    transport = "fv3_halo_exchange_nccl" if pc.nccl_comm is not None else "torch.distributed"
+    want = os.environ.get("FV3_EXPECT_TRANSPORT")
+    if want and want != transport:
+        failures.append(f"halo messages went through {transport}, expected {want}")
     print(f"[rank {pc.rank}] {case}: reference ranks checked {sorted(mine)}, worst relative error {worst:.2e}, "
-          f"{len(failures)} failures", flush=True)
+          f"halo messages via {transport}, {len(failures)} failures", flush=True)
     for f in failures[:10]:
         print(f"[rank {pc.rank}]   {f}", flush=True)
     bad = torch.tensor([len(failures)], dtype=torch.int64, device=dev)
