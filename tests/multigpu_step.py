@@ -1,5 +1,5 @@
 """One strict step case on SEVERAL GPUs (launched by torch.distributed.run, one process per GPU): the inter-GPU halo path
-(fv3_halo_pack_segments -> fv3_halo_exchange_nccl, or torch.distributed send/recv with FV3_NATIVE_NCCL=0 ->
+(fv3_halo_pack_segments -> torch.distributed send/recv, or fv3_halo_exchange_nccl with FV3_NATIVE_NCCL=1 ->
 fv3_halo_unpack_segments on the communication stream) against the
 reference's final state.  Every process checks the reference ranks it owns; exit code 0 = all within tolerance.
 

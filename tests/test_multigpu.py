@@ -23,18 +23,18 @@ def _launch(nproc, case, extra_env=None, port=29531):
 @pytest.mark.gpu
 @pytest.mark.parametrize("nproc", [2, 4])
 def test_strict_step_over_nccl(nproc):
-    """Messages through the C ABI (fv3_halo_exchange_nccl on the library's own ncclComm_t): the default on NCCL groups."""
+    """Messages through the C ABI (fv3_halo_exchange_nccl on the library's own ncclComm_t; FV3_NATIVE_NCCL=1)."""
     if torch.cuda.device_count() < nproc:
         pytest.skip(f"needs {nproc} GPUs")
-    _launch(nproc, "c24L2k2n3", {"FV3_EXPECT_TRANSPORT": "fv3_halo_exchange_nccl"}, port=29530 + nproc)
+    _launch(nproc, "c24L2k2n3", {"FV3_NATIVE_NCCL": "1", "FV3_EXPECT_TRANSPORT": "fv3_halo_exchange_nccl"}, port=29530 + nproc)
 
 
 @pytest.mark.gpu
 def test_strict_step_over_torch_distributed_p2p():
-    """The same case with the messages posted through torch.distributed.batch_isend_irecv (FV3_NATIVE_NCCL=0)."""
+    """The same case with the messages posted through torch.distributed.batch_isend_irecv (the default transport)."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    _launch(2, "c24L2k2n3", {"FV3_NATIVE_NCCL": "0", "FV3_EXPECT_TRANSPORT": "torch.distributed"}, port=29537)
+    _launch(2, "c24L2k2n3", {"FV3_EXPECT_TRANSPORT": "torch.distributed"}, port=29537)
 
 
 def test_strict_step_over_gloo_two_processes():
