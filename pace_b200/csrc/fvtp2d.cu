@@ -8,12 +8,6 @@
 // corner copies are index remaps at read time (ppm.h), every intermediate lives in shared memory.
 #include "transport.h"
 
-#ifndef FV3_TR_TCACHE
-#define FV3_TR_TCACHE 0
-#endif
-#ifndef FV3_TR_EARLY
-#define FV3_TR_EARLY 1
-#endif
 
 namespace {
 
@@ -148,9 +142,6 @@ int fv3_tracer_subcycle(fv3_ctx *ctx, double *const *tracers, int nq, double *dp
     const int64_t ob = O3(s, 0, 0, k), o2b = O2(s, 0, 0);
     const double *rarea = m.rarea + o2b;
     b.prefetch_next_wave(tracers[0], g, k);
-#if FV3_TR_TCACHE
-    b.prefetch_rows(dp1 + ob, sj);
-#endif
     b.bulk_begin(1, sj);
     b.bulk_rows(Q, tracers[0] + ob, sj);
     for (int n = 0; n < nq; ++n) {
@@ -158,49 +149,26 @@ int fv3_tracer_subcycle(fv3_ctx *ctx, double *const *tracers, int nq, double *dp
       if (n + 1 < nq) b.prefetch_rows(tracers[n + 1] + ob, sj);  // HBM -> L2 now, L2 -> shared memory after the sweeps
       const PlaneArgs pa{q, cx, cy, xfx, yfx, mfx, mfy};
       fvtp2d_plane<8, true, true>(g, m, s, k, b, pa, Q, A, B, D, T);
-#if FV3_TR_EARLY
       // Q (q advected along y) is dead once the outer sweeps are done: the next tracer's rows arrive during the update
       if (n + 1 < nq) {
         b.bulk_begin(1, sj);
         b.bulk_rows(Q, tracers[n + 1] + ob, sj);
       }
-#endif
       b.rect(h, h + nx, b.ja, b.jb, [&](int i, int j) {
         const int p = j * sj + i;
         const int64_t o = ob + p;
         const double d1 = dp1[o];
-#if FV3_TR_TCACHE
-        // the new mass (apply_mass_flux :115-135) is formed by the first tracer's update and kept in the free plane T
-        double d2;
-        if (n == 0) {
-          d2 = d1 + (mfx[o] - mfx[o + 1] + mfy[o] - mfy[o + sj]) * rarea[p];
-          T[p] = d2;
-        } else {
-          d2 = T[p];
-        }
-#else
         const double d2 = d1 + (mfx[o] - mfx[o + 1] + mfy[o] - mfy[o + sj]) * rarea[p];
-#endif
         // rows another strip of this plane reads as halo are parked in a side buffer (in-place update)
         const bool parked = (j < b.ja + h && b.ja > h) || (j >= b.jb - h && !b.last);
         (parked ? side0 + n * side_stride : q)[o] = (q[o] * d1 + (B[p] - B[p + 1] + A[p] - A[p + sj]) * rarea[p]) / d2;
       });
-#if !FV3_TR_EARLY
-      if (n + 1 < nq) {
-        b.bulk_begin(1, sj);
-        b.bulk_rows(Q, tracers[n + 1] + ob, sj);
-      }
-#endif
     }
     b.rect(h, h + nx, b.ja, b.jb, [&](int i, int j) {
       const int p = j * sj + i;
       const int64_t o = ob + p;
       const double d1 = dp1[o];
-#if FV3_TR_TCACHE
-      const double d2 = T[p];
-#else
       const double d2 = d1 + (mfx[o] - mfx[o + 1] + mfy[o] - mfy[o + sj]) * rarea[p];
-#endif
       if (swap) {
         dp1[o] = d2;
         dp2[o] = d1;
