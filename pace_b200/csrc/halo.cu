@@ -6,7 +6,10 @@
 #include "common.h"
 
 namespace {
-constexpr int HALO_KB = 8;
+#ifndef FV3_HALO_KB
+#define FV3_HALO_KB 8
+#endif
+constexpr int HALO_KB = FV3_HALO_KB;  // levels moved per thread
 }
 
 extern "C" {

@@ -14,6 +14,9 @@
 
 namespace fv3 {
 
+#ifndef FV3_HORD8_AL
+#define FV3_HORD8_AL 0
+#endif
 #ifndef FV3_SWEEP_R
 #define FV3_SWEEP_R 4
 #endif
@@ -61,6 +64,15 @@ FV_HD double ppm_face_8(double c, bool pos, double qm, double q0, double qq, dou
   const double xt = 2.0 * dm0;
   const double alc = 0.5 * (qm + q0) + 1.0 / 3.0 * (dmm - dm0);
   const double alr = 0.5 * (q0 + qq) + 1.0 / 3.0 * (dm0 - dmp);
+  const double bl = -1.0 * rsign(dmin(fabs(xt), fabs(alc - q0)), xt);
+  const double br = rsign(dmin(fabs(xt), fabs(alr - q0)), xt);
+  const double b0 = bl + br;
+  return pos ? q0 + (1.0 - c) * (br - c * b0) : q0 + (1.0 + c) * (bl + c * b0);
+}
+
+// the same with the edge values of the upwind cell given (alc = left, alr = right)
+FV_HD double ppm_face_8al(double c, bool pos, double q0, double dm0, double alc, double alr) {
+  const double xt = 2.0 * dm0;
   const double bl = -1.0 * rsign(dmin(fabs(xt), fabs(alc - q0)), xt);
   const double br = rsign(dmin(fabs(xt), fabs(alr - q0)), xt);
   const double b0 = bl + br;
@@ -173,6 +185,22 @@ struct Sweep {
         double dm[R + 3];
 #pragma unroll
         for (int m = 0; m < R + 3; ++m) dm[m] = ppm_dm8v(w[m + 1], w[m + 2], w[m + 3]);
+#if FV3_HORD8_AL
+        // edge values at the faces F0-1 .. F0+R, ONCE per face: al[m] (face F0 - 1 + m) is the right edge of cell
+        // F0 - 2 + m and the left edge of cell F0 - 1 + m (the two expressions of ppm_face_8 coincide there)
+        double al[R + 2];
+#pragma unroll
+        for (int m = 0; m < R + 2; ++m) al[m] = 0.5 * (w[m + 2] + w[m + 3]) + 1.0 / 3.0 * (dm[m] - dm[m + 1]);
+#pragma unroll
+        for (int n = 0; n < R; ++n) {
+          if ((unsigned)(F0 + n - fv0) > nfv) continue;
+          const bool pos = c[n] > 0.0;
+          // upwind cell: f - 1 (w[n + 3], dm[n + 1], faces al[n], al[n + 1]) for c > 0, else f (w[n + 4], dm[n + 2], al[n + 1], al[n + 2])
+          const double q0 = pos ? w[n + 3] : w[n + 4], dm0 = pos ? dm[n + 1] : dm[n + 2];
+          const double alc = pos ? al[n] : al[n + 1], alr = pos ? al[n + 1] : al[n + 2];
+          fin(p0 + n * st, ppm_face_8al(c[n], pos, q0, dm0, alc, alr));
+        }
+#else
 #pragma unroll
         for (int n = 0; n < R; ++n) {
           if ((unsigned)(F0 + n - fv0) > nfv) continue;
@@ -182,6 +210,7 @@ struct Sweep {
           const double dmm = pos ? dm[n] : dm[n + 1], dm0 = pos ? dm[n + 1] : dm[n + 2], dmp = pos ? dm[n + 2] : dm[n + 3];
           fin(p0 + n * st, ppm_face_8(c[n], pos, qm, q0, qq, dmm, dm0, dmp));
         }
+#endif
       }
     } else {
       // faces next to a cube-tile edge: one-sided edge values / bl, br (xppm.py:148-181, 185-246).  One task per
