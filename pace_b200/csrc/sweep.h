@@ -14,9 +14,6 @@
 
 namespace fv3 {
 
-#ifndef FV3_HORD8_AL
-#define FV3_HORD8_AL 0
-#endif
 #ifndef FV3_SWEEP_R
 #define FV3_SWEEP_R 4
 #endif
@@ -59,18 +56,9 @@ FV_HD double ppm_dm8v(double qm, double q0, double qq) {
   const double dql = q0 - dmin(dmin(q0, qm), qq);
   return rsign(dmin(dmin(fabs(xt), dqr), dql), xt);
 }
-// hord 8: qm, q0, qq = upwind cell and its neighbours, dmm, dm0, dmp their limited slopes
-FV_HD double ppm_face_8(double c, bool pos, double qm, double q0, double qq, double dmm, double dm0, double dmp) {
-  const double xt = 2.0 * dm0;
-  const double alc = 0.5 * (qm + q0) + 1.0 / 3.0 * (dmm - dm0);
-  const double alr = 0.5 * (q0 + qq) + 1.0 / 3.0 * (dm0 - dmp);
-  const double bl = -1.0 * rsign(dmin(fabs(xt), fabs(alc - q0)), xt);
-  const double br = rsign(dmin(fabs(xt), fabs(alr - q0)), xt);
-  const double b0 = bl + br;
-  return pos ? q0 + (1.0 - c) * (br - c * b0) : q0 + (1.0 + c) * (bl + c * b0);
-}
-
-// the same with the edge values of the upwind cell given (alc = left, alr = right)
+// hord 8: q0, dm0 = upwind cell and its limited slope, alc / alr = edge values at its left / right face (xppm.py:82-102,
+// 74-79); an edge value is shared by the two cells it separates, so the sweep forms it once per face (measured: tracer
+// sub-cycle 3405 -> 3330 us, bit-identical)
 FV_HD double ppm_face_8al(double c, bool pos, double q0, double dm0, double alc, double alr) {
   const double xt = 2.0 * dm0;
   const double bl = -1.0 * rsign(dmin(fabs(xt), fabs(alc - q0)), xt);
@@ -185,9 +173,8 @@ struct Sweep {
         double dm[R + 3];
 #pragma unroll
         for (int m = 0; m < R + 3; ++m) dm[m] = ppm_dm8v(w[m + 1], w[m + 2], w[m + 3]);
-#if FV3_HORD8_AL
         // edge values at the faces F0-1 .. F0+R, ONCE per face: al[m] (face F0 - 1 + m) is the right edge of cell
-        // F0 - 2 + m and the left edge of cell F0 - 1 + m (the two expressions of ppm_face_8 coincide there)
+        // F0 - 2 + m and the left edge of cell F0 - 1 + m (alc of one cell and alr of its neighbour are the same expression there)
         double al[R + 2];
 #pragma unroll
         for (int m = 0; m < R + 2; ++m) al[m] = 0.5 * (w[m + 2] + w[m + 3]) + 1.0 / 3.0 * (dm[m] - dm[m + 1]);
@@ -200,17 +187,6 @@ struct Sweep {
           const double alc = pos ? al[n] : al[n + 1], alr = pos ? al[n + 1] : al[n + 2];
           fin(p0 + n * st, ppm_face_8al(c[n], pos, q0, dm0, alc, alr));
         }
-#else
-#pragma unroll
-        for (int n = 0; n < R; ++n) {
-          if ((unsigned)(F0 + n - fv0) > nfv) continue;
-          const bool pos = c[n] > 0.0;
-          // upwind cell: f - 1 (w[n + 3], dm[n + 1]) for c > 0, else f (w[n + 4], dm[n + 2])
-          const double qm = pos ? w[n + 2] : w[n + 3], q0 = pos ? w[n + 3] : w[n + 4], qq = pos ? w[n + 4] : w[n + 5];
-          const double dmm = pos ? dm[n] : dm[n + 1], dm0 = pos ? dm[n + 1] : dm[n + 2], dmp = pos ? dm[n + 2] : dm[n + 3];
-          fin(p0 + n * st, ppm_face_8(c[n], pos, qm, q0, qq, dmm, dm0, dmp));
-        }
-#endif
       }
     } else {
       // faces next to a cube-tile edge: one-sided edge values / bl, br (xppm.py:148-181, 185-246).  One task per
