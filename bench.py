@@ -455,6 +455,8 @@ def main():
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args), "clocks": clocks,
         "halo_transport": ("device-local gathers only" if world == 1 else
                            ("fv3_halo_exchange_nccl (C ABI, own ncclComm_t)" if pc.nccl_comm is not None else "torch.distributed.batch_isend_irecv")),
+        # per-stage device time of the eager pass (CUDA events around every C-ABI call), per timestep, largest first
+        "stages_ms_per_step": {name: round(t_ms / n_eager, 4) for t_ms, n, name in table[:14]},
         "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "fp64_peak_tflops": fp64_peak, "finite": finite,
         "state_digest": digest,
         "launch_mode": mode, "ms_per_step_eager": ms_eager, "host_enqueue_ms_per_step": host_enqueue_ms,
