@@ -613,14 +613,16 @@ void unpark_rows(const fv3_ctx *ctx, cudaStream_t st, Fields4 fl, int nf, double
   });
 }
 
-// ---- K2: the four flux-form transports of d_sw (delp, w, q_con, pt) and everything between them, ONE strip-resident
-// kernel (d_sw.py:967-1090): delp transport + del-n damping -> mass fluxes (kept in a scratch field that stays in L2,
+// ---- K2: the four flux-form transports of d_sw (delp, w, q_con, pt) and everything between them, strip-resident
+// (d_sw.py:967-1090): delp transport + del-n damping -> mass fluxes (kept in a scratch field that stays in L2,
 // accumulated into mfx / mfy: flux_capacitor :29-50); del-n fluxes of damp_w * w and the heat they dissipate (:53-103);
 // w, q_con, pt transports with the mass fluxes, their del-n damping, and the flux-form updates of all four fields
-// (apply_fluxes, apply_pt_delp_fluxes, adjust_w_and_qcon :106-160,331-346).  Compulsory traffic: 4 fields read and
-// written, 4 Courant / area-flux fields read, mfx / mfy read-modify-write, heat written.
-// The eight steps run as ONE loop around a single transport body and a single del-n body (a step table selects the
-// field and the operands), so that the kernel holds one copy of each sweep instead of four.
+// (apply_fluxes, apply_pt_delp_fluxes, adjust_w_and_qcon :106-160,331-346).
+// ONE source, instantiated per PARTS (bit mask: 1 delp, 2 w, 4 q_con, 8 pt and the new mass): the stage runs as four
+// kernels of 7.7-8.5 K SASS instructions (FV3_K2_SPLIT = 4) — measured faster than two (PARTS 3, 12) or one (15, 38 K
+// instructions) although every kernel stages crx / cry / xfx / yfx / delp again; the mass fluxes and the old delp are
+// read-only after the first part, so the parts only have to run in order.  Within a part the sequence is straight-line
+// (field pointers and column parameters stay kernel-parameter constants).
 // MDP / MVT / MTM: |hord_dp|, |hord_vt|, |hord_tm| (5, 6 or 8).
 template <int MDP, int MVT, int MTM, int PARTS = 15>
 int dsw_scalars_launch(fv3_ctx *ctx, cudaStream_t st, double *delp, double *pt, double *w, double *q_con, const double *crx,
